@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — Lanczos iterations/s on BASELINE.json's config 2 (2-D 5-point Laplacian 4096x4096, CSR, double, 4 smallest
+eigenpairs), measured on the GPU(s) and, beside it, on the host CPU with the reference implementation.
+
+A "step" is one complete ``LambdaLanczos::run()`` on that operator with ``max_iteration`` capped (the algorithm stores
+every Lanczos vector — 134 MB each here — so natural convergence, ~16k vectors, fits no machine):
+two Lanczos runs of ``max_iteration`` iterations (the second deflated against the 4 kept vectors) plus eigenvector
+assembly.  value = Lanczos iterations / second over the timed steps.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (see the keys below).  ``--impl reference`` times the UNMODIFIED reference (oracle/_ref, compiled
+from /root/reference; falls back to the oracle's C restatement) on the host cores on a bounded sample of the same
+workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lanczos_iterations_per_second"
+UNIT = "iterations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4096, help="grid side of the Laplacian (config 2: 4096)")
+    ap.add_argument("--max-iteration", type=int, default=192, help="cap on Lanczos iterations per run (basis must fit HBM)")
+    ap.add_argument("--num-eigs", type=int, default=4)
+    ap.add_argument("--cpu-sample-iterations", type=int, default=0, help="max_iteration of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_name(args):
+    return (f"config2: 2-D 5-point Laplacian {args.nx}x{args.nx} (n={args.nx * args.nx}) CSR double, {args.num_eigs} smallest "
+            f"eigenpairs, full reorthogonalisation, max_iteration={args.max_iteration} per Lanczos run")
+
+
+def bytes_model(n, s, a_bytes, counts, num_eigs, nroot=5):
+    """B_run = m*A_bytes + (m(m+1) + (2q+7)m) n s + (m + r) n s, summed over the Lanczos runs."""
+    total = 0.0
+    q = 0
+    for m in counts:
+        total += m * a_bytes + (m * (m + 1) + (2 * q + 7) * m) * n * s + (m + nroot) * n * s
+        q = min(num_eigs, q + nroot)
+    return total
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on the host cores, bounded sample of the workload."""
+    if rank != 0:
+        return
+    import __graft_entry__ as entry
+    import importlib
+
+    entry.load_package()
+    wl = importlib.import_module("lambda_lanczos_b200.workloads")
+    import oracle
+
+    impl = oracle.best()
+    threads = impl.host_threads() if hasattr(impl, "host_threads") else 1
+    n = args.nx * args.nx
+    csr = wl.laplacian2d_csr(args.nx)
+    start = wl.start_vector(n)
+    kw = dict(find_max=False, num_eigs=args.num_eigs, init=start)
+    if impl.kind == "reference":
+        kw.update(mv_threads=threads, want_vectors=False)
+    m = args.cpu_sample_iterations
+    if m <= 0:
+        # calibrate on a 3-iteration probe: cost ~ c * m^2 per run; keep (steps + warmup) runs within ~150 s
+        t0 = time.perf_counter()
+        impl.lanczos(*csr, max_iter=3, **kw)
+        probe = time.perf_counter() - t0
+        budget = 150.0 / max(1, args.steps + args.warmup)
+        m = int(max(4, min(16, 3 * (budget / max(probe, 1e-3)) ** 0.5)))
+    iters = 0
+    for _ in range(args.warmup):
+        impl.lanczos(*csr, max_iter=m, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = impl.lanczos(*csr, max_iter=m, **kw)
+        iters += sum(r.iter_counts)
+    dt = time.perf_counter() - t0
+    value = iters / dt
+    sample = (f"same operator and start vector, max_iteration={m} per Lanczos run ({len(r.iter_counts)} runs/step); mv_mul "
+              f"CSR lambda on {threads} thread(s), the reference's vector kernels are single-threaded")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": impl.kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, wl, csr, start):
+    import oracle
+
+    impl = oracle.best()
+    threads = impl.host_threads() if hasattr(impl, "host_threads") else 1
+    kw = dict(find_max=False, num_eigs=args.num_eigs, init=start)
+    if impl.kind == "reference":
+        kw.update(mv_threads=threads, want_vectors=False)
+    m = args.cpu_sample_iterations if args.cpu_sample_iterations > 0 else 8
+    t0 = time.perf_counter()
+    r = impl.lanczos(*csr, max_iter=m, **kw)
+    dt = time.perf_counter() - t0
+    return {"value": sum(r.iter_counts) / dt, "unit": UNIT, "cores": threads, "kind": impl.kind,
+            "sample": f"one run() of the same workload with max_iteration={m} ({sum(r.iter_counts)} iterations, {dt:.1f} s); "
+                      f"mv_mul on {threads} thread(s), reference vector kernels single-threaded"}
+
+
+def run_ours(args, rank, world):
+    import importlib
+
+    import torch
+
+    import __graft_entry__ as entry
+
+    pkg = entry.load_package()
+    wl = importlib.import_module("lambda_lanczos_b200.workloads")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    n = args.nx * args.nx
+    csr = wl.laplacian2d_csr(args.nx)
+    start = wl.start_vector(n)
+    if world > 1:
+        raise SystemExit("row-sharded multi-GPU runs are wired in a later commit")
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: operator already in HBM, eigenvectors stay on the device ----
+    op = pkg.Operator.csr(ctx, *csr)
+    eng = pkg.LambdaLanczos(op, n, False, args.num_eigs)
+    eng.init_vector = start
+    eng.max_iteration = args.max_iteration
+    eng.want_eigenvectors = False
+    for _ in range(args.warmup):
+        eng.run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))  # the engine's own stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    iters = 0
+    counts = []
+    host_s = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        evals, _ = eng.run()
+        counts = eng.getIterationCounts()
+        iters += sum(counts)
+        host_s += eng.stats.seconds_host
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dt = ev0.elapsed_time(ev1) * 1e-3  # device time of the K steps on the launching stream (host control included)
+    launches = ctx.launch_count() - launches0
+    prof = {name: ctx.profile_read(name) for name in ("spmv", "project", "reduce", "update", "scale", "combine", "dot")}
+    ctx.profile(False)
+    clocks = sampler.stop()
+    value = iters / dt
+
+    # ---- roofline of the dominant kernel family (the two basis-streaming GEMV passes) ----
+    peak, peak_src = load_measured_peak()
+    dom = max(("project", "update"), key=lambda k: prof[k][0])
+    ms, cnt, by = prof[dom]
+    achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    s = 8
+    model_bytes = bytes_model(n, s, op.bytes(), counts, args.num_eigs) * args.steps
+    roofline = {"bound": "hbm", "kernel": f"k_{dom}<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "launches": cnt, "avg_launch_ms": ms / max(cnt, 1), "algorithmic_bytes_per_launch": by / max(cnt, 1),
+                "kernel_time_share": {k: v[0] / (dt * 1e3) for k, v in prof.items() if v[1] > 0},
+                "whole_step_model_GBps": model_bytes / dt / 1e9, "whole_step_frac_of_peak": model_bytes / dt / 1e9 / peak}
+
+    # ---- end-to-end arm: host CSR arrays in, host eigenvectors out, every step ----
+    del eng, op
+    barrier()
+    e2e_iters = 0
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        op2 = pkg.Operator.csr(ctx, *csr)  # H2D of the operator
+        eng2 = pkg.LambdaLanczos(op2, n, False, args.num_eigs)
+        eng2.init_vector = start
+        eng2.max_iteration = args.max_iteration
+        evals2, evecs2 = eng2.run()  # H2D start vectors, D2H eigenvectors
+        e2e_iters += sum(eng2.getIterationCounts())
+        runs = len(eng2.getIterationCounts())
+        del eng2, op2
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    h2d = csr[0].nbytes // 2 + csr[1].nbytes + csr[2].nbytes + runs * start.nbytes  # row pointers travel as int32
+    d2h = evecs2.nbytes + 16 * e2e_iters // e2e_steps
+    e2e = {"value": e2e_iters / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "seconds_per_step": e2e_dt / e2e_steps}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "iterations_per_step": sum(counts), "lanczos_runs_per_step": len(counts),
+                       "l2": "inputs (basis of up to %d x 134 MB) far exceed the 126 MB L2" % (args.max_iteration + 1),
+                       "time_to_eigenpair_s": dt / args.steps, "wall_seconds_per_step": wall / args.steps, "host_seconds_per_step": host_s / args.steps,
+                       "eigenvalues": [float(x) for x in evals]},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, wl, csr, start)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

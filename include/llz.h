@@ -1,0 +1,217 @@
+/* llz.h — C ABI of the B200-native Lanczos engine (libllz.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of mrcdr/lambda-lanczos: the Krylov iteration inside
+ * LambdaLanczos<T>::run and Exponentiator<T>::run.  Plain pointers and sizes only; no C++ or torch types.
+ * Every entry point names the reference interface (file:line under /root/reference/include/lambda_lanczos/) that it
+ * replaces.  The reference has no FFI of its own (it is a header-only C++ library); the C++ header
+ * lambda-lanczos_b200/include/lambda_lanczos_b200/lambda_lanczos.hpp rebuilds the reference's classes on top of
+ * exactly these calls, and INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns an llz_status_t (0 = OK); llz_last_error() gives the message for the calling thread;
+ *   - dtype selects the scalar type T of vectors and operators; alpha/beta/eigenvalues/eps/offset are always passed
+ *     as double across this ABI (real_t<T> of the reference, util/common.hpp:80-102);
+ *   - complex scalars are interleaved (re, im) pairs, layout-compatible with std::complex<> and C99 _Complex;
+ *   - "device pointer" arguments must be 16-byte aligned device memory on the context's GPU;
+ *   - one context = one GPU + one stream (+ one rank of a row-sharded group); a context is not thread-safe, the
+ *     reference engine objects are not either (lambda_lanczos.hpp:331,395-403).
+ *   - there is NO CPU fallback: without a usable CUDA device llz_ctx_create fails with LLZ_ERR_NO_DEVICE.
+ */
+#ifndef LLZ_H_
+#define LLZ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLZ_VERSION 100 /* 0.1.0 */
+
+typedef struct llz_ctx_s* llz_ctx_t;
+typedef struct llz_op_s* llz_op_t;
+typedef struct llz_vec_s* llz_vec_t;
+typedef struct llz_krylov_s* llz_krylov_t;
+
+typedef enum {
+  LLZ_F32 = 0,  /* float                */
+  LLZ_F64 = 1,  /* double               */
+  LLZ_C64 = 2,  /* std::complex<float>  */
+  LLZ_C128 = 3  /* std::complex<double> */
+} llz_dtype_t;
+
+typedef enum {
+  LLZ_OK = 0,
+  LLZ_ERR_INVALID = 1,     /* bad argument / shape / dtype */
+  LLZ_ERR_CUDA = 2,        /* CUDA runtime or driver error */
+  LLZ_ERR_OOM = 3,         /* device memory exhausted (e.g. the Krylov basis cannot grow further) */
+  LLZ_ERR_COMM = 4,        /* inter-GPU communication error */
+  LLZ_ERR_UNSUPPORTED = 5, /* valid request this build cannot serve */
+  LLZ_ERR_NO_DEVICE = 6,   /* no CUDA device: the engine has no CPU path */
+  LLZ_ERR_USER = 7         /* a user callback reported failure */
+} llz_status_t;
+
+/* How llz_krylov_step orthogonalises the new Lanczos vector. */
+typedef enum {
+  LLZ_ORTH_RECURRENCE = 0, /* three-term recurrence only          (exponentiator.hpp:112-118, full_orthogonalize=false) */
+  LLZ_ORTH_FULL = 1,       /* recurrence + one classical Gram-Schmidt pass against [locked, basis]
+                              (replaces the MGS sweeps of lambda_lanczos.hpp:259-260, exponentiator.hpp:120-122) */
+  LLZ_ORTH_FULL_TWICE = 2  /* as FULL, followed by a second projection pass (CGS2) */
+} llz_orth_t;
+
+int llz_version(void);
+const char* llz_status_string(int status);
+const char* llz_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------------------------- */
+int llz_ctx_create(int device, llz_ctx_t* ctx);
+/* Same, but launch everything on a caller-owned cudaStream_t (passed as void*). */
+int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* ctx);
+int llz_ctx_destroy(llz_ctx_t ctx);
+int llz_ctx_synchronize(llz_ctx_t ctx);
+int llz_ctx_stream(llz_ctx_t ctx, void** cuda_stream);
+/* Number of kernels this context has launched so far (the bench's "gpu_launches" evidence). */
+int llz_ctx_launch_count(llz_ctx_t ctx, uint64_t* count);
+/* Per-kernel-family device time (CUDA events on the context's stream) accumulated since profiling was last switched
+ * on.  Families: "spmv", "dot", "project", "reduce", "update", "recurrence", "scale", "combine".  `bytes` is the
+ * algorithmic traffic of the timed launches (SURVEY.md §8d accounting), so bytes/ms is the achieved bandwidth. */
+int llz_ctx_profile(llz_ctx_t ctx, int enable);
+int llz_ctx_profile_read(llz_ctx_t ctx, const char* name, double* ms, int64_t* launches, double* bytes);
+/* Join a row-sharded group of `nranks` contexts (one per GPU, one process each).  `comm_id` is the 128-byte blob
+ * produced by llz_comm_unique_id on rank 0 and distributed by the caller (e.g. torch.distributed / MPI / a file).
+ * Afterwards every vector is the local row block of a global vector and all reductions are group-wide. */
+int llz_comm_unique_id(void* id128);
+int llz_ctx_join(llz_ctx_t ctx, int rank, int nranks, const void* id128);
+int llz_ctx_rank(llz_ctx_t ctx, int* rank, int* nranks);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Operators — the device-side replacement of the `mv_mul` std::function
+ * (lambda_lanczos.hpp:120-126, exponentiator.hpp:35-41).  Contract kept: one apply per iteration, never concurrent.
+ * Built-in operators OVERWRITE y (the reference pre-zeroes `out`, lambda_lanczos.hpp:242, and lets the callee
+ * accumulate; y = 0 + A x is the same result without the extra pass).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* CSR with 32-bit column indices.  Arrays are copied to the device (host_arrays != 0) or adopted by copy from device
+ * memory (host_arrays == 0).  In a joined context `n_rows` is the local row block starting at global row `row0`, and
+ * column indices are global. */
+int llz_op_create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
+                      const int32_t* colidx, const void* vals, int host_arrays, llz_op_t* op);
+/* Matrix-free spin-1/2 XXZ chain  H = sum_b Jxy/2 (S+S- + h.c.) + Jz SzSz  on L sites in the sector with n_up up
+ * spins, basis states in increasing integer order (BASELINE.json configs 4 and 5). */
+int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, double jz, double jxy, int periodic, llz_op_t* op);
+/* User operator.  `apply` must enqueue y (+)= A x on `cuda_stream` and return 0.  If overwrites_y == 0 the engine
+ * zero-fills y first, as the reference promises its callee (lambda_lanczos.hpp:124). */
+typedef int (*llz_apply_fn)(void* user, const void* x_dev, void* y_dev, int64_t n_local, void* cuda_stream);
+int llz_op_create_callback(llz_ctx_t ctx, int dtype, int64_t n_local, llz_apply_fn apply, void* user,
+                           int overwrites_y, llz_op_t* op);
+int llz_op_destroy(llz_op_t op);
+int llz_op_rows(llz_op_t op, int64_t* n_local);
+/* Algorithmic bytes one apply has to move for the operator itself (A_bytes of SURVEY.md §8d; 0 for matrix-free). */
+int llz_op_bytes(llz_op_t op, int64_t* bytes);
+/* y = A x on device vectors (stand-alone use and Exponentiator::taylor_run, exponentiator.hpp:191). */
+int llz_op_apply(llz_op_t op, llz_vec_t x, llz_vec_t y);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device vectors and the util:: vector kernels (util/linear_algebra.hpp)
+ * ---------------------------------------------------------------------------------------------------------------- */
+int llz_vec_create(llz_ctx_t ctx, int dtype, int64_t n_local, llz_vec_t* v);
+int llz_vec_destroy(llz_vec_t v);
+int llz_vec_upload(llz_vec_t v, const void* host);  /* H2D, n_local elements */
+int llz_vec_download(llz_vec_t v, void* host);      /* D2H (synchronises the stream) */
+int llz_vec_device_ptr(llz_vec_t v, void** dev);
+int llz_vec_copy(llz_vec_t dst, llz_vec_t src);
+int llz_vec_fill_zero(llz_vec_t v);
+/* out[0..1] = <a,b> = sum conj(a_i) b_i   (util::inner_prod, linear_algebra.hpp:30-51; conjugates the FIRST argument) */
+int llz_vec_dot(llz_vec_t a, llz_vec_t b, double out[2]);
+/* *out = sqrt(Re<v,v>)                     (util::norm, linear_algebra.hpp:57-60) */
+int llz_vec_norm(llz_vec_t v, double* out);
+/* v *= a                                   (util::scalar_mul, linear_algebra.hpp:66-72) */
+int llz_vec_scale(llz_vec_t v, const double a[2]);
+/* v *= 1/norm(v), *norm_out = norm before  (util::normalize, linear_algebra.hpp:78-80) */
+int llz_vec_normalize(llz_vec_t v, double* norm_out);
+/* y += a x */
+int llz_vec_axpy(llz_vec_t y, const double a[2], llz_vec_t x);
+/* w -= sum_j <u_j,w> u_j over `count` orthonormal vectors (util::schmidt_orth, linear_algebra.hpp:133-144), done as
+ * `passes` classical Gram-Schmidt passes (projection V^H w, then update w - V h) instead of the reference's
+ * vector-by-vector modified Gram-Schmidt. */
+int llz_vec_schmidt_orth(llz_vec_t w, const llz_vec_t* basis, int64_t count, int passes);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Krylov workspace — the device-resident Lanczos basis (`u`, lambda_lanczos.hpp:221; exponentiator.hpp:90) plus the
+ * alpha/beta recurrences (:222-223).  Column-major, one allocation, columns 256-byte aligned, grown on demand.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* max_cols: upper bound on stored Lanczos vectors (max_iteration + 1); the store reserves address space for
+ * min(max_cols, what fits in device memory) columns and maps physical memory as the iteration advances. */
+int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n_local, int64_t max_cols, llz_krylov_t* kry);
+int llz_krylov_destroy(llz_krylov_t kry);
+/* Largest number of columns this workspace can ever hold (address space and device memory permitting). */
+int llz_krylov_capacity(llz_krylov_t kry, int64_t* max_cols);
+/* Vectors every new Lanczos vector is additionally orthogonalised against (`orthogonalizeTo`,
+ * lambda_lanczos.hpp:220,233,259): the eigenvectors kept by earlier runs.  The handles must stay alive. */
+int llz_krylov_set_locked(llz_krylov_t kry, const llz_vec_t* locked, int64_t count);
+/* Start a run: column 0 := start (host pointer if host != 0, else device pointer), orthogonalised against the locked
+ * vectors, normalised (lambda_lanczos.hpp:231-234; exponentiator.hpp:100-101).  *norm_out = norm before normalising. */
+int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm_out);
+/* Enqueue Lanczos iteration k = ncols (1-based as in lambda_lanczos.hpp:240):
+ *   w = (A + sigma I) u_{k-1}; alpha_{k-1} = Re<u_{k-1}, w>                  (:242-248, exponentiator.hpp:107-110)
+ *   u_k = w - alpha u_{k-1} - beta_{k-2} u_{k-2}, orthogonalised per `orth`  (:250-260, exponentiator.hpp:112-122)
+ *   beta_{k-1} = ||u_k||; u_k /= beta_{k-1}                                  (:262,285, exponentiator.hpp:145,160)
+ * Asynchronous: returns once the work is queued; the scalars arrive through llz_krylov_fetch. */
+int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth);
+/* Block until iteration k (1-based) has finished and return alpha_{k-1}, beta_{k-1}. */
+int llz_krylov_fetch(llz_krylov_t kry, int64_t k, double* alpha, double* beta);
+/* Number of iterations enqueued so far (stored columns = this + 1). */
+int llz_krylov_steps(llz_krylov_t kry, int64_t* k);
+/* out_r = sum_{j<m} coeff[r*m + j] u_j for r < nvec, optionally normalised — the eigenvector assembly of
+ * compute_eigenvectors (lambda_lanczos.hpp:51-58) and the Exponentiator's output sum (exponentiator.hpp:163-170) in
+ * ONE pass over the basis.  coeff is a host array of T (interleaved complex), out are device vectors. */
+int llz_krylov_combine(llz_krylov_t kry, int64_t m, int64_t nvec, const void* coeff, int normalize,
+                       const llz_vec_t* out);
+/* Device pointer of column j (for tests: the oracle's Lanczos vectors are observable through its mv_mul spy). */
+int llz_krylov_column_ptr(llz_krylov_t kry, int64_t j, void** dev);
+int llz_krylov_download_column(llz_krylov_t kry, int64_t j, void* host);
+/* ------------------------------------------------------------------------------------------------------------------
+ * Whole-engine entry points (what a non-C++ caller binds): the host control loop of the reference, restated in
+ * lambda_lanczos_b200/lambda_lanczos.hpp and exponentiator.hpp, instantiated for the four dtypes.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int find_maximum;               /* lambda_lanczos.hpp:153 */
+  int64_t num_eigs;               /* :156 */
+  double eigenvalue_offset;       /* :165 */
+  double eps;                     /* :150; <= 0 selects the reference default 1e3*machine-eps of real_t<T> */
+  int64_t max_iteration;          /* :138; <= 0 selects matrix_size */
+  int64_t num_eigs_per_iteration; /* :173; <= 0 selects 5 */
+  int orth;                       /* llz_orth_t; the reference behaviour is LLZ_ORTH_FULL */
+  int pipeline_depth;             /* iterations the GPU may run ahead of the host convergence test (0 = lock-step) */
+  int ritz_solver;                /* 0 = bisection on the nroot extreme Ritz values, 1 = full implicit QL every step */
+} llz_eigs_params_t;
+
+typedef struct {
+  double seconds_total;    /* wall time of the run, host clock */
+  double seconds_host;     /* host tridiagonal solves + convergence logic */
+  int64_t iterations;      /* Lanczos iterations over all runs */
+  int64_t runs;            /* Lanczos runs (lambda_lanczos.hpp:334 loop) */
+  int64_t basis_bytes;     /* peak bytes of the mapped Krylov basis */
+  uint64_t kernel_launches;
+} llz_run_stats_t;
+
+/* LambdaLanczos<T>(op, n, find_maximum, num_eigs).run(eigenvalues, eigenvectors)  (lambda_lanczos.hpp:200,330-366).
+ * start: host vector handed out by `init_vector` at the start of every Lanczos run (:133,232); NULL selects a seeded
+ * uniform[-1,1] vector.  eigenvalues_out: num_eigs doubles.  eigenvectors_out: host, num_eigs x n_local elements of T
+ * (may be NULL).  iter_counts: getIterationCounts() (:412), at most max_runs entries. */
+int llz_eigs_run(llz_ctx_t ctx, llz_op_t op, int dtype, const llz_eigs_params_t* params, const void* start,
+                 double* eigenvalues_out, void* eigenvectors_out, int64_t* n_found, int64_t* iter_counts,
+                 int64_t max_runs, int64_t* n_runs, llz_run_stats_t* stats);
+
+/* Exponentiator<T>(op, n).run(a, input, output)  (exponentiator.hpp:80,87-173): output = exp(a A) input.
+ * a is (re, im); im is ignored for real dtypes.  input/output are host vectors (host != 0) or device pointers.
+ * eps <= 0 selects 1e2*machine-eps (:58); max_iteration <= 0 selects n (:81).  taylor != 0 runs taylor_run (:175). */
+int llz_expm_run(llz_ctx_t ctx, llz_op_t op, int dtype, const double a[2], const void* input, void* output, int host,
+                 double eps, int full_orthogonalize, int64_t max_iteration, int taylor, int64_t* iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLZ_H_ */

@@ -1,0 +1,339 @@
+// llz_ctx.cu — contexts, error reporting, device vectors and the stand-alone util:: vector operations.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "llz_launch.hpp"
+
+namespace llz {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+}  // namespace llz
+
+using namespace llz;
+
+extern "C" {
+
+int llz_version(void) { return LLZ_VERSION; }
+
+const char* llz_status_string(int status) {
+  switch (status) {
+    case LLZ_OK: return "ok";
+    case LLZ_ERR_INVALID: return "invalid argument";
+    case LLZ_ERR_CUDA: return "CUDA error";
+    case LLZ_ERR_OOM: return "out of device memory";
+    case LLZ_ERR_COMM: return "communication error";
+    case LLZ_ERR_UNSUPPORTED: return "unsupported";
+    case LLZ_ERR_NO_DEVICE: return "no CUDA device (this engine has no CPU path)";
+    case LLZ_ERR_USER: return "user callback failed";
+  }
+  return "unknown status";
+}
+
+const char* llz_last_error(void) { return g_error; }
+
+int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* out) {
+  if (!out) return fail(LLZ_ERR_INVALID, "ctx_create: null output");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(LLZ_ERR_NO_DEVICE, "no usable CUDA device (%s); the engine has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(LLZ_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  LLZ_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LLZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(LLZ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  llz_ctx_t ctx = new llz_ctx_s();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  if (cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return fail(LLZ_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+  }
+  LLZ_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * kMaxGrid * 2));
+  LLZ_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * 8));
+  LLZ_CUDA(cudaHostAlloc(&ctx->h_result, sizeof(double) * 8, cudaHostAllocDefault));
+  *out = ctx;
+  return LLZ_OK;
+}
+
+int llz_ctx_create(int device, llz_ctx_t* out) { return llz_ctx_create_on_stream(device, nullptr, out); }
+
+int llz_ctx_synchronize(llz_ctx_t ctx) {
+  if (!ctx) return fail(LLZ_ERR_INVALID, "null ctx");
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LLZ_OK;
+}
+
+int llz_ctx_stream(llz_ctx_t ctx, void** s) {
+  if (!ctx || !s) return fail(LLZ_ERR_INVALID, "null argument");
+  *s = (void*)ctx->stream;
+  return LLZ_OK;
+}
+
+int llz_ctx_launch_count(llz_ctx_t ctx, uint64_t* count) {
+  if (!ctx || !count) return fail(LLZ_ERR_INVALID, "null argument");
+  *count = ctx->launches;
+  return LLZ_OK;
+}
+
+int llz_ctx_profile(llz_ctx_t ctx, int enable) {
+  if (!ctx) return fail(LLZ_ERR_INVALID, "null ctx");
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& kv : ctx->prof) {
+    for (auto& p : kv.second.pending) {
+      ctx->event_pool.push_back(p.first);
+      ctx->event_pool.push_back(p.second);
+    }
+    kv.second = ProfEntry();
+  }
+  ctx->profile = enable != 0;
+  return LLZ_OK;
+}
+
+int llz_ctx_profile_read(llz_ctx_t ctx, const char* name, double* ms, int64_t* launches, double* bytes) {
+  if (!ctx || !name) return fail(LLZ_ERR_INVALID, "null");
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  double total = 0.0, by = 0.0;
+  int64_t count = 0;
+  auto it = ctx->prof.find(name);
+  if (it != ctx->prof.end()) {
+    for (auto& p : it->second.pending) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) it->second.ms += t;
+      ctx->event_pool.push_back(p.first);
+      ctx->event_pool.push_back(p.second);
+    }
+    it->second.pending.clear();
+    total = it->second.ms;
+    count = it->second.launches;
+    by = it->second.bytes;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = count;
+  if (bytes) *bytes = by;
+  return LLZ_OK;
+}
+
+int llz_ctx_rank(llz_ctx_t ctx, int* rank, int* nranks) {
+  if (!ctx) return fail(LLZ_ERR_INVALID, "null ctx");
+  if (rank) *rank = ctx->rank;
+  if (nranks) *nranks = ctx->nranks;
+  return LLZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int llz_vec_create(llz_ctx_t ctx, int dtype, int64_t n, llz_vec_t* out) {
+  if (!ctx || !out || n < 0 || dtype_size(dtype) == 0) return fail(LLZ_ERR_INVALID, "vec_create: bad argument");
+  LLZ_CUDA(cudaSetDevice(ctx->device));
+  llz_vec_t v = new llz_vec_s();
+  v->ctx = ctx;
+  v->dtype = dtype;
+  v->n = n;
+  const size_t bytes = ((size_t)n * dtype_size(dtype) + 255) / 256 * 256 + 256;
+  cudaError_t e = cudaMalloc(&v->d, bytes);
+  if (e != cudaSuccess) {
+    delete v;
+    return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "cudaMalloc(%zu): %s", bytes,
+                cudaGetErrorString(e));
+  }
+  *out = v;
+  return LLZ_OK;
+}
+
+int llz_vec_destroy(llz_vec_t v) {
+  if (!v) return LLZ_OK;
+  if (v->owned && v->d) {
+    cudaStreamSynchronize(v->ctx->stream);
+    cudaFree(v->d);
+  }
+  delete v;
+  return LLZ_OK;
+}
+
+int llz_vec_upload(llz_vec_t v, const void* host) {
+  if (!v || !host) return fail(LLZ_ERR_INVALID, "vec_upload: null");
+  LLZ_CUDA(cudaMemcpyAsync(v->d, host, (size_t)v->n * dtype_size(v->dtype), cudaMemcpyHostToDevice, v->ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return LLZ_OK;
+}
+
+int llz_vec_download(llz_vec_t v, void* host) {
+  if (!v || !host) return fail(LLZ_ERR_INVALID, "vec_download: null");
+  LLZ_CUDA(cudaMemcpyAsync(host, v->d, (size_t)v->n * dtype_size(v->dtype), cudaMemcpyDeviceToHost, v->ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return LLZ_OK;
+}
+
+int llz_vec_device_ptr(llz_vec_t v, void** dev) {
+  if (!v || !dev) return fail(LLZ_ERR_INVALID, "null");
+  *dev = v->d;
+  return LLZ_OK;
+}
+
+int llz_vec_copy(llz_vec_t dst, llz_vec_t src) {
+  if (!dst || !src || dst->n != src->n || dst->dtype != src->dtype) return fail(LLZ_ERR_INVALID, "vec_copy: mismatch");
+  LLZ_CUDA(cudaMemcpyAsync(dst->d, src->d, (size_t)src->n * dtype_size(src->dtype), cudaMemcpyDeviceToDevice,
+                           dst->ctx->stream));
+  return LLZ_OK;
+}
+
+int llz_vec_fill_zero(llz_vec_t v) {
+  if (!v) return fail(LLZ_ERR_INVALID, "null");
+  LLZ_CUDA(cudaMemsetAsync(v->d, 0, (size_t)v->n * dtype_size(v->dtype), v->ctx->stream));
+  return LLZ_OK;
+}
+
+static int dot_to_host(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double out[2]) {
+  int grid = 0;
+  const int nc = dtype_nc(dtype);
+  LLZ_TRY(launch_dot(ctx, dtype, a, b, n, ctx->d_partials, &grid));
+  LLZ_TRY(launch_sum_partials(ctx, ctx->d_partials, grid, nc, ctx->d_result, nullptr));
+  LLZ_TRY(comm_allreduce_sum(ctx, ctx->d_result, nc));
+  LLZ_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  out[0] = ctx->h_result[0];
+  out[1] = nc == 2 ? ctx->h_result[1] : 0.0;
+  return LLZ_OK;
+}
+
+int llz_vec_dot(llz_vec_t a, llz_vec_t b, double out[2]) {
+  if (!a || !b || !out || a->n != b->n || a->dtype != b->dtype) return fail(LLZ_ERR_INVALID, "vec_dot: mismatch");
+  return dot_to_host(a->ctx, a->dtype, a->d, b->d, a->n, out);
+}
+
+int llz_vec_norm(llz_vec_t v, double* out) {
+  if (!v || !out) return fail(LLZ_ERR_INVALID, "null");
+  double d[2];
+  LLZ_TRY(dot_to_host(v->ctx, v->dtype, v->d, v->d, v->n, d));
+  *out = sqrt(d[0]);
+  return LLZ_OK;
+}
+
+int llz_vec_scale(llz_vec_t v, const double a[2]) {
+  if (!v || !a) return fail(LLZ_ERR_INVALID, "null");
+  return launch_scale(v->ctx, v->dtype, v->d, v->n, a);
+}
+
+int llz_vec_normalize(llz_vec_t v, double* norm_out) {
+  if (!v) return fail(LLZ_ERR_INVALID, "null");
+  double nrm = 0.0;
+  LLZ_TRY(llz_vec_norm(v, &nrm));
+  if (norm_out) *norm_out = nrm;
+  // T(1)/norm in the working precision, as util::normalize does (linear_algebra.hpp:78-80)
+  const bool single = (v->dtype == LLZ_F32 || v->dtype == LLZ_C64);
+  const double inv[2] = {single ? (double)(1.0f / (float)nrm) : 1.0 / nrm, 0.0};
+  return launch_scale(v->ctx, v->dtype, v->d, v->n, inv);
+}
+
+int llz_vec_axpy(llz_vec_t y, const double a[2], llz_vec_t x) {
+  if (!y || !x || !a || y->n != x->n || y->dtype != x->dtype) return fail(LLZ_ERR_INVALID, "vec_axpy: mismatch");
+  return launch_axpy(y->ctx, y->dtype, y->d, a, x->d, y->n);
+}
+
+int llz_vec_schmidt_orth(llz_vec_t w, const llz_vec_t* basis, int64_t count, int passes) {
+  if (!w || count < 0 || (count > 0 && !basis)) return fail(LLZ_ERR_INVALID, "schmidt_orth: bad argument");
+  if (count == 0) return LLZ_OK;
+  llz_ctx_t ctx = w->ctx;
+  const int nc = dtype_nc(w->dtype);
+  if (passes < 1) passes = 1;
+  // pointer table + coefficient / partial buffers, grown on demand
+  if (count > ctx->ptr_capacity) {
+    if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
+    if (ctx->d_coef) cudaFree(ctx->d_coef);
+    ctx->d_ptrs = nullptr;
+    ctx->d_coef = nullptr;
+    int64_t cap = count < 64 ? 64 : count * 2;
+    LLZ_CUDA(cudaMalloc(&ctx->d_ptrs, sizeof(void*) * cap));
+    LLZ_CUDA(cudaMalloc(&ctx->d_coef, sizeof(double) * 2 * cap));
+    ctx->ptr_capacity = cap;
+  }
+  std::vector<const void*> ptrs((size_t)count);
+  for (int64_t j = 0; j < count; ++j) {
+    if (!basis[j] || basis[j]->n != w->n || basis[j]->dtype != w->dtype)
+      return fail(LLZ_ERR_INVALID, "schmidt_orth: basis vector %lld mismatched", (long long)j);
+    ptrs[(size_t)j] = basis[j]->d;
+  }
+  LLZ_CUDA(cudaMemcpyAsync(ctx->d_ptrs, ptrs.data(), sizeof(void*) * count, cudaMemcpyHostToDevice, ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));  // ptrs is a stack-lifetime staging buffer
+  const int chunk = max_project_cols(w->dtype);
+  const size_t need = (size_t)kMaxGrid * (size_t)(count < chunk ? count : chunk) * nc;
+  if (need > ctx->ph_capacity) {
+    if (ctx->d_ph) cudaFree(ctx->d_ph);
+    ctx->d_ph = nullptr;
+    LLZ_CUDA(cudaMalloc(&ctx->d_ph, sizeof(double) * need));
+    ctx->ph_capacity = need;
+  }
+  ColumnSet cs;
+  cs.Q = (const void* const*)ctx->d_ptrs;
+  cs.nq = (int)count;
+  Fold nofold;
+  for (int p = 0; p < passes; ++p) {
+    for (int c0 = 0; c0 < count; c0 += chunk) {
+      const int nc_cols = (int)((count - c0) < chunk ? (count - c0) : chunk);
+      int grid = 0;
+      LLZ_TRY(launch_project(ctx, w->dtype, cs, c0, nc_cols, w->d, w->n, nofold, ctx->d_ph, &grid));
+      LLZ_TRY(launch_reduce(ctx, w->dtype, ctx->d_ph, grid, c0, nc_cols, ctx->d_coef, -1, nullptr, -1, nullptr));
+    }
+    LLZ_TRY(comm_allreduce_sum(ctx, ctx->d_coef, (int)count * nc));
+    const int uchunk = max_update_cols(w->dtype);
+    for (int c0 = 0; c0 < count; c0 += uchunk) {
+      const int nc_cols = (int)((count - c0) < uchunk ? (count - c0) : uchunk);
+      int grid = 0;
+      LLZ_TRY(launch_update(ctx, w->dtype, cs, c0, nc_cols, w->d, w->d, w->n, ctx->d_coef, nullptr, &grid));
+    }
+  }
+  return LLZ_OK;
+}
+
+int llz_ctx_destroy(llz_ctx_t ctx) {
+  if (!ctx) return LLZ_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_result) cudaFree(ctx->d_result);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
+  if (ctx->d_coef) cudaFree(ctx->d_coef);
+  if (ctx->d_ph) cudaFree(ctx->d_ph);
+  for (auto& kv : ctx->prof)
+    for (auto& p : kv.second.pending) {
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LLZ_OK;
+}
+
+}  // extern "C"

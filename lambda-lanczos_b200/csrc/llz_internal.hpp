@@ -1,0 +1,148 @@
+// llz_internal.hpp — host-side object definitions behind the opaque handles of include/llz.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/llz.h"
+
+namespace llz {
+
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+
+#define LLZ_CUDA(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return ::llz::fail(e__ == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                         cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+  } while (0)
+
+#define LLZ_TRY(expr)             \
+  do {                            \
+    int s__ = (expr);             \
+    if (s__ != LLZ_OK) return s__; \
+  } while (0)
+
+inline size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case LLZ_F32: return 4;
+    case LLZ_F64: return 8;
+    case LLZ_C64: return 8;
+    case LLZ_C128: return 16;
+  }
+  return 0;
+}
+inline int dtype_nc(int dtype) { return (dtype == LLZ_C64 || dtype == LLZ_C128) ? 2 : 1; }
+
+struct Comm;  // inter-GPU plumbing (llz_comm.cu)
+
+// Per-kernel device-time accounting (CUDA events on the context's stream), keyed by a short kernel-family name.
+struct ProfEntry {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  double ms = 0.0;
+  int64_t launches = 0;
+  double bytes = 0.0;  // algorithmic bytes the timed launches had to move (SURVEY.md §8d accounting)
+};
+
+}  // namespace llz
+
+struct llz_ctx_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  size_t l2_bytes = 0;
+  uint64_t launches = 0;
+  int rank = 0, nranks = 1;
+  llz::Comm* comm = nullptr;
+  // scratch shared by the stand-alone vector kernels: per-CTA partials + pinned result slot
+  double* d_partials = nullptr;  // kMaxGrid * 2 doubles
+  double* d_result = nullptr;    // 8 doubles
+  double* h_result = nullptr;    // pinned, 8 doubles
+  void** d_ptrs = nullptr;       // pointer table for llz_vec_schmidt_orth
+  double* d_coef = nullptr;      // coefficients for llz_vec_schmidt_orth
+  double* d_ph = nullptr;        // h partials for llz_vec_schmidt_orth
+  size_t ph_capacity = 0;
+  int64_t ptr_capacity = 0;
+  // profiling
+  bool profile = false;
+  std::map<std::string, llz::ProfEntry> prof;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+struct llz_vec_s {
+  llz_ctx_t ctx = nullptr;
+  int dtype = 0;
+  int64_t n = 0;
+  void* d = nullptr;
+  bool owned = true;
+};
+
+namespace llz {
+
+constexpr int kMaxGrid = 4096;  // upper bound on the grid of any persistent kernel (=> on per-CTA partial arrays)
+
+// Operator interface (device side of the reference's mv_mul)
+struct OpBase {
+  llz_ctx_t ctx = nullptr;
+  int dtype = 0;
+  int64_t n_local = 0;
+  int64_t bytes = 0;
+  virtual ~OpBase() {}
+  // y = A x + sigma x ; per-CTA partials of Re<x,y> into alpha_partials[0..*n_partials) (device), all on ctx->stream.
+  // Returns LLZ_OK or an error.  Implementations that cannot fuse the dot leave *n_partials = 0 and the engine runs
+  // a separate dot kernel.
+  virtual int apply_fused(const void* x, void* y, double sigma, double* alpha_partials, int* n_partials) = 0;
+};
+
+}  // namespace llz
+
+namespace llz {
+// Group-wide sums over the row-sharded ranks (no-ops for a single rank).  `d` is device memory on ctx->stream.
+int comm_allreduce_sum(llz_ctx_t ctx, double* d, int count);
+// Per-CTA partials of a scalar: leaves them alone for one rank; otherwise folds them to one group-wide value
+// (d[0], *count = 1).
+int comm_allreduce_partials(llz_ctx_t ctx, double* d, int* count);
+void comm_destroy(llz_ctx_t ctx);
+
+// RAII: records a start/stop event pair around the launches issued in its scope when ctx->profile is on.
+struct ProfScope {
+  llz_ctx_t ctx;
+  ProfEntry* entry = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(llz_ctx_t c, const char* name, double bytes) : ctx(c) {
+    if (!c->profile) return;
+    entry = &c->prof[name];
+    entry->bytes += bytes;
+    e0 = take();
+    e1 = take();
+    cudaEventRecord(e0, c->stream);
+  }
+  cudaEvent_t take() {
+    if (!ctx->event_pool.empty()) {
+      cudaEvent_t e = ctx->event_pool.back();
+      ctx->event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ~ProfScope() {
+    if (!entry) return;
+    cudaEventRecord(e1, ctx->stream);
+    entry->pending.emplace_back(e0, e1);
+    entry->launches++;
+  }
+};
+}  // namespace llz
+
+struct llz_op_s {
+  llz::OpBase* impl = nullptr;
+};

@@ -1,0 +1,836 @@
+// llz_kernels.cu — the bandwidth-bound streaming kernels of the Lanczos iteration (sm_100a).
+//
+//   k_project      h = [Q,V]^H w'        tall-skinny GEMV-T, w' = w - alpha u_{k-1} - beta u_{k-2} folded in registers
+//   k_reduce       coef = sum over CTAs of the h partials (+ recurrence coefficients)
+//   k_update       u_k = w - [Q,V] coef  tall-skinny GEMV-N, ||u_k||^2 partials in the epilogue
+//   k_scale_norm   u_k *= 1/beta, publishes alpha/beta to the device bank and the pinned host mirror
+//   k_recurrence   u_k = w - alpha u_{k-1} - beta u_{k-2} (+ norm partials)  [no reorthogonalisation]
+//   k_combine      out_r = sum_j y_r[j] u_j for up to 5 vectors in one pass over the basis
+//   k_dot, k_scale, k_axpy, k_sum_partials   the util:: vector helpers
+//
+// Together k_project + k_reduce + k_update replace the reference's modified Gram-Schmidt sweep
+// (util::schmidt_orth, util/linear_algebra.hpp:133-144, called at lambda_lanczos.hpp:259-260): two streaming passes
+// over the basis instead of 2k dependent vector passes.  Every kernel is persistent (grid <= SMs x resident CTAs),
+// walks contiguous row slabs with 128-bit loads, keeps the w slab in registers across all columns, and reduces in a
+// fixed order (no floating-point atomics), so results are reproducible bit for bit.
+#include <algorithm>
+
+#include "llz_device.cuh"
+#include "llz_launch.hpp"
+
+namespace llz {
+
+constexpr int CT = 8;  // columns per register tile
+
+// ------------------------------------------------------------------------------------------------------------------
+struct ProjectArgs {
+  const void* V;
+  int64_t ld;
+  const void* const* Q;
+  int nq;
+  int col0, ncols;
+  const void* w;
+  int64_t n;
+  int fold;
+  const double* pa;
+  int npa;
+  const double* beta_prev;
+  double* alpha_out;
+  const void* u1;  // V[:, nv-1]
+  const void* u2;  // V[:, nv-2]
+  double* ph;
+};
+
+template <class T> __device__ __forceinline__ const T* column_ptr(const void* V, int64_t ld, const void* const* Q, int nq, int j) {
+  return (j < nq) ? reinterpret_cast<const T*>(Q[j]) : reinterpret_cast<const T*>(V) + (int64_t)(j - nq) * ld;
+}
+
+template <class T, int VPT, bool FULL>
+__device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base, typename Num<T>::R alpha,
+                                             typename Num<T>::R beta, double* hs_warp, int lane) {
+  using R = typename Num<T>::R;
+  constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC, M = CT * NC;
+  const int tid = threadIdx.x;
+  const T* w = reinterpret_cast<const T*>(a.w);
+
+  Pack<T> wp[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+    wp[i] = FULL ? ld_stream(w + idx) : ld_guard(w, idx, a.n);
+  }
+  if (a.fold >= 1) {
+    const T* u1 = reinterpret_cast<const T*>(a.u1);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+      Pack<T> v = FULL ? ld_stream(u1 + idx) : ld_guard(u1, idx, a.n);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fnma_real(wp[i].e[e], alpha, v.e[e]);
+    }
+    if (a.fold >= 2) {
+      const T* u2 = reinterpret_cast<const T*>(a.u2);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+        Pack<T> v = FULL ? ld_stream(u2 + idx) : ld_guard(u2, idx, a.n);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fnma_real(wp[i].e[e], beta, v.e[e]);
+      }
+    }
+  }
+
+  for (int j0 = 0; j0 < a.ncols; j0 += CT) {
+    T acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[c] = zero_of(T());
+    if (j0 + CT <= a.ncols) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const T* col = column_ptr<T>(a.V, a.ld, a.Q, a.nq, a.col0 + j0 + c);
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+          const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+          Pack<T> v = FULL ? ld_stream(col + idx) : ld_guard(col, idx, a.n);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) fma_conj(acc[c], v.e[e], wp[i].e[e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        if (j0 + c < a.ncols) {
+          const T* col = column_ptr<T>(a.V, a.ld, a.Q, a.nq, a.col0 + j0 + c);
+#pragma unroll
+          for (int i = 0; i < VPT; ++i) {
+            const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+            Pack<T> v = FULL ? ld_stream(col + idx) : ld_guard(col, idx, a.n);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) fma_conj(acc[c], v.e[e], wp[i].e[e]);
+          }
+        }
+      }
+    }
+    R red[M];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) red[k * CT + c] = comp(acc[c], k);
+    warp_transpose_sum<M>(red, lane);
+    if (transpose_is_writer<M>(lane)) {
+      const int v = transpose_owner_index<M>(lane);
+      const int c = v % CT, k = v / CT;
+      if (j0 + c < a.ncols) hs_warp[(j0 + c) * NC + k] += (double)red[0];
+    }
+  }
+}
+
+template <class T, int VPT>
+__global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
+  using R = typename Num<T>::R;
+  constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
+  extern __shared__ __align__(16) double smem_d[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int width = a.ncols * NC;
+  double* hs = smem_d;                     // [kWarps][width]
+  double* scratch = smem_d + kWarps * width;  // [kWarps]
+  for (int i = tid; i < kWarps * width; i += kThreads) hs[i] = 0.0;
+
+  R alpha = 0, beta = 0;
+  if (a.fold >= 1) {
+    const double al = block_sum_partials(a.pa, a.npa, scratch);
+    alpha = (R)al;
+    if (blockIdx.x == 0 && tid == 0 && a.alpha_out) *a.alpha_out = al;
+    if (a.fold >= 2) beta = (R)(*a.beta_prev);
+  }
+  __syncthreads();
+
+  constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
+  const int64_t nslabs = (a.n + SLAB - 1) / SLAB;
+  double* hs_warp = hs + warp * width;
+  for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
+    const int64_t base = s * SLAB;
+    if (base + SLAB <= a.n)
+      project_slab<T, VPT, true>(a, base, alpha, beta, hs_warp, lane);
+    else
+      project_slab<T, VPT, false>(a, base, alpha, beta, hs_warp, lane);
+  }
+  __syncthreads();
+  double* out = a.ph + (size_t)blockIdx.x * width;
+  for (int i = tid; i < width; i += kThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int wi = 0; wi < kWarps; ++wi) s += hs[wi * width + i];
+    out[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct ReduceArgs {
+  const double* ph;
+  int grid;
+  int width;  // ncols*NC of the chunk
+  double* coef;  // already offset to the chunk
+  int i_alpha;   // index (in doubles, within the chunk) receiving +alpha, or -1
+  const double* alpha;
+  int i_beta;
+  const double* beta_prev;
+};
+
+__global__ void __launch_bounds__(128) k_reduce(ReduceArgs a) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= a.width) return;
+  double s = 0.0;
+  for (int c = 0; c < a.grid; ++c) s += a.ph[(size_t)c * a.width + i];
+  if (i == a.i_alpha) s += *a.alpha;
+  if (i == a.i_beta) s += *a.beta_prev;
+  a.coef[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct UpdateArgs {
+  const void* V;
+  int64_t ld;
+  const void* const* Q;
+  int nq;
+  int col0, ncols;
+  const void* w;
+  void* out;
+  int64_t n;
+  const double* coef;  // full coefficient array (indexed by absolute column)
+  double* pb;          // norm partials or null
+};
+
+template <class T, int VPT, bool FULL>
+__device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base, const T* cs) {
+  constexpr int VEC = Num<T>::VEC;
+  const int tid = threadIdx.x;
+  const T* w = reinterpret_cast<const T*>(a.w);
+  T* out = reinterpret_cast<T*>(a.out);
+  Pack<T> acc[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+    acc[i] = FULL ? ld_plain(w + idx) : ld_guard(w, idx, a.n);
+  }
+  int j0 = 0;
+  for (; j0 + CT <= a.ncols; j0 += CT) {
+    Pack<T> v[CT][VPT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const T* col = column_ptr<T>(a.V, a.ld, a.Q, a.nq, a.col0 + j0 + c);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+        v[c][i] = FULL ? ld_stream(col + idx) : ld_guard(col, idx, a.n);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const T cj = cs[j0 + c];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fnma(acc[i].e[e], cj, v[c][i].e[e]);
+    }
+  }
+  for (; j0 < a.ncols; ++j0) {
+    const T* col = column_ptr<T>(a.V, a.ld, a.Q, a.nq, a.col0 + j0);
+    const T cj = cs[j0];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+      Pack<T> v = FULL ? ld_stream(col + idx) : ld_guard(col, idx, a.n);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fnma(acc[i].e[e], cj, v.e[e]);
+    }
+  }
+  double nrm = 0.0;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+    if (FULL)
+      st_pack(out + idx, acc[i]);
+    else
+      st_guard(out, idx, a.n, acc[i]);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) nrm += abs2(acc[i].e[e]);  // guarded lanes hold zeros
+  }
+  return nrm;
+}
+
+template <class T, int VPT>
+__global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
+  constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
+  extern __shared__ __align__(16) unsigned char smem_u[];
+  T* cs = reinterpret_cast<T*>(smem_u);
+  __shared__ double scratch[kWarps];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.ncols; i += kThreads) {
+    const double* c = a.coef + (size_t)(a.col0 + i) * NC;
+    cs[i] = from_double<T>(c[0], NC == 2 ? c[NC - 1] : 0.0);
+  }
+  __syncthreads();
+  constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
+  const int64_t nslabs = (a.n + SLAB - 1) / SLAB;
+  double nrm = 0.0;
+  for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
+    const int64_t base = s * SLAB;
+    nrm += (base + SLAB <= a.n) ? update_slab<T, VPT, true>(a, base, cs) : update_slab<T, VPT, false>(a, base, cs);
+  }
+  if (a.pb) {
+    const double t = block_sum(nrm, scratch);
+    if (tid == 0) a.pb[blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct ScaleNormArgs {
+  void* x;
+  int64_t n;
+  const double* pb;
+  int npb;
+  ScalarSink sink;
+};
+
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(ScaleNormArgs a) {
+  using R = typename Num<T>::R;
+  constexpr int VEC = Num<T>::VEC;
+  __shared__ double scratch[kWarps];
+  const int tid = threadIdx.x;
+  const double beta2 = block_sum_partials(a.pb, a.npb, scratch);
+  const double beta = sqrt(beta2);
+  if (blockIdx.x == 0 && tid == 0) {
+    if (a.sink.beta_out) *a.sink.beta_out = beta;
+    if (a.sink.h_beta) *a.sink.h_beta = beta;
+    if (a.sink.h_alpha && a.sink.alpha_in) *a.sink.h_alpha = *a.sink.alpha_in;
+    if (a.sink.h_flag) {
+      __threadfence_system();
+      *reinterpret_cast<volatile long long*>(a.sink.h_flag) = a.sink.flag_value;
+    }
+  }
+  if (!(beta > 0.0) || !isfinite(beta)) return;  // breakdown: the reference leaves u_k un-normalised (:279-283)
+  const R inv = (R)1 / (R)beta;                   // normalize() multiplies by T(1)/norm (linear_algebra.hpp:78-80)
+  T* x = reinterpret_cast<T*>(a.x);
+  const int64_t npacks = a.n / VEC;
+  for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < npacks; p += (int64_t)gridDim.x * kThreads) {
+    Pack<T> v = ld_plain(x + p * VEC);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v.e[e] = scale_real(v.e[e], inv);
+    st_pack(x + p * VEC, v);
+  }
+  if (blockIdx.x == 0) {
+    const int64_t i = npacks * VEC + tid;
+    if (i < a.n) x[i] = scale_real(x[i], inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct RecurrenceArgs {
+  const void* w;
+  const void* u1;
+  const void* u2;
+  void* out;
+  int64_t n;
+  int fold;
+  const double* pa;
+  int npa;
+  const double* beta_prev;
+  double* alpha_out;
+  double* pb;
+};
+
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
+  using R = typename Num<T>::R;
+  constexpr int VEC = Num<T>::VEC;
+  __shared__ double scratch[kWarps];
+  const int tid = threadIdx.x;
+  R alpha = 0, beta = 0;
+  if (a.fold >= 1) {
+    const double al = block_sum_partials(a.pa, a.npa, scratch);
+    alpha = (R)al;
+    if (blockIdx.x == 0 && tid == 0 && a.alpha_out) *a.alpha_out = al;
+    if (a.fold >= 2) beta = (R)(*a.beta_prev);
+  }
+  const T* w = reinterpret_cast<const T*>(a.w);
+  const T* u1 = reinterpret_cast<const T*>(a.u1);
+  const T* u2 = reinterpret_cast<const T*>(a.u2);
+  T* out = reinterpret_cast<T*>(a.out);
+  const int64_t npacks = (a.n + VEC - 1) / VEC;
+  double nrm = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < npacks; p += (int64_t)gridDim.x * kThreads) {
+    const int64_t idx = p * VEC;
+    const bool full = idx + VEC <= a.n;
+    Pack<T> acc = full ? ld_plain(w + idx) : ld_guard(w, idx, a.n);
+    if (a.fold >= 1) {
+      Pack<T> v = full ? ld_stream(u1 + idx) : ld_guard(u1, idx, a.n);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fnma_real(acc.e[e], alpha, v.e[e]);
+    }
+    if (a.fold >= 2) {
+      Pack<T> v = full ? ld_stream(u2 + idx) : ld_guard(u2, idx, a.n);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fnma_real(acc.e[e], beta, v.e[e]);
+    }
+    if (full)
+      st_pack(out + idx, acc);
+    else
+      st_guard(out, idx, a.n, acc);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) nrm += abs2(acc.e[e]);
+  }
+  if (a.pb) {
+    const double t = block_sum(nrm, scratch);
+    if (tid == 0) a.pb[blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxCombine = 5;  // num_eigs_per_iteration default (lambda_lanczos.hpp:173)
+
+struct CombineArgs {
+  const void* V;
+  int64_t ld;
+  int col0, ncols;
+  const void* coef;  // device, T[nvec][ldc]
+  int64_t ldc;
+  int nvec;
+  void* out[kMaxCombine];
+  int64_t n;
+  int accumulate;
+  double* pb;  // [nvec][kMaxGrid] or null
+};
+
+template <class T, int NV, bool FULL>
+__device__ __forceinline__ void combine_slab(const CombineArgs& a, int64_t base, const T* cs, double (&nrm)[NV]) {
+  constexpr int VEC = Num<T>::VEC;
+  const int tid = threadIdx.x;
+  const int64_t idx = base + (int64_t)tid * VEC;
+  Pack<T> acc[NV];
+#pragma unroll
+  for (int r = 0; r < NV; ++r) {
+    if (a.accumulate && r < a.nvec) {
+      const T* o = reinterpret_cast<const T*>(a.out[r]);
+      acc[r] = FULL ? ld_plain(o + idx) : ld_guard(o, idx, a.n);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[r].e[e] = zero_of(T());
+    }
+  }
+  const T* V = reinterpret_cast<const T*>(a.V) + (int64_t)a.col0 * a.ld;
+  int j0 = 0;
+  for (; j0 + 4 <= a.ncols; j0 += 4) {
+    Pack<T> v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const T* col = V + (int64_t)(j0 + c) * a.ld;
+      v[c] = FULL ? ld_stream(col + idx) : ld_guard(col, idx, a.n);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < NV; ++r) {
+        const T y = cs[r * a.ncols + j0 + c];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fmadd(acc[r].e[e], y, v[c].e[e]);
+      }
+  }
+  for (; j0 < a.ncols; ++j0) {
+    const T* col = V + (int64_t)j0 * a.ld;
+    Pack<T> v = FULL ? ld_stream(col + idx) : ld_guard(col, idx, a.n);
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+      const T y = cs[r * a.ncols + j0];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fmadd(acc[r].e[e], y, v.e[e]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NV; ++r) {
+    if (r < a.nvec) {
+      T* o = reinterpret_cast<T*>(a.out[r]);
+      if (FULL)
+        st_pack(o + idx, acc[r]);
+      else
+        st_guard(o, idx, a.n, acc[r]);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) nrm[r] += abs2(acc[r].e[e]);
+    }
+  }
+}
+
+template <class T, int NV> __global__ void __launch_bounds__(kThreads, 2) k_combine(CombineArgs a) {
+  constexpr int VEC = Num<T>::VEC;
+  extern __shared__ __align__(16) unsigned char smem_c[];
+  T* cs = reinterpret_cast<T*>(smem_c);  // [NV][ncols], zero rows beyond nvec
+  __shared__ double scratch[kWarps];
+  const int tid = threadIdx.x;
+  const T* coef = reinterpret_cast<const T*>(a.coef);
+  for (int i = tid; i < NV * a.ncols; i += kThreads) {
+    const int r = i / a.ncols, j = i % a.ncols;
+    cs[i] = (r < a.nvec) ? coef[(int64_t)r * a.ldc + a.col0 + j] : zero_of(T());
+  }
+  __syncthreads();
+  constexpr int64_t SLAB = (int64_t)kThreads * VEC;
+  const int64_t nslabs = (a.n + SLAB - 1) / SLAB;
+  double nrm[NV];
+#pragma unroll
+  for (int r = 0; r < NV; ++r) nrm[r] = 0.0;
+  for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
+    const int64_t base = s * SLAB;
+    if (base + SLAB <= a.n)
+      combine_slab<T, NV, true>(a, base, cs, nrm);
+    else
+      combine_slab<T, NV, false>(a, base, cs, nrm);
+  }
+  if (a.pb) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+      if (r < a.nvec) {
+        const double t = block_sum(nrm[r], scratch);
+        if (tid == 0) a.pb[(size_t)r * kMaxGrid + blockIdx.x] = t;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_dot(const T* __restrict__ x, const T* __restrict__ y, int64_t n, double* partials) {
+  constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
+  __shared__ double scratch[kWarps];
+  const int tid = threadIdx.x;
+  T acc = zero_of(T());
+  double re = 0.0, im = 0.0;
+  const int64_t npacks = (n + VEC - 1) / VEC;
+  for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < npacks; p += (int64_t)gridDim.x * kThreads) {
+    const int64_t idx = p * VEC;
+    const bool full = idx + VEC <= n;
+    Pack<T> a = full ? ld_plain(x + idx) : ld_guard(x, idx, n);
+    Pack<T> b = full ? ld_plain(y + idx) : ld_guard(y, idx, n);
+    acc = zero_of(T());
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) fma_conj(acc, a.e[e], b.e[e]);
+    re += (double)comp(acc, 0);
+    if (NC == 2) im += (double)comp(acc, 1);
+  }
+  const double tre = block_sum(re, scratch);
+  if (tid == 0) partials[(size_t)blockIdx.x * NC] = tre;
+  if (NC == 2) {
+    const double tim = block_sum(im, scratch);
+    if (tid == 0) partials[(size_t)blockIdx.x * NC + 1] = tim;
+  }
+}
+
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const T* __restrict__ x, const T* __restrict__ y, int64_t n, double* partials) {
+  constexpr int VEC = Num<T>::VEC;
+  __shared__ double scratch[kWarps];
+  double re = 0.0;
+  const int64_t npacks = (n + VEC - 1) / VEC;
+  for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < npacks; p += (int64_t)gridDim.x * kThreads) {
+    const int64_t idx = p * VEC;
+    const bool full = idx + VEC <= n;
+    Pack<T> a = full ? ld_plain(x + idx) : ld_guard(x, idx, n);
+    Pack<T> b = full ? ld_plain(y + idx) : ld_guard(y, idx, n);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) re += re_conj_mul(a.e[e], b.e[e]);
+  }
+  const double t = block_sum(re, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// result[c] = sum_i partials[i*nc + c]; also mirrored to pinned host memory when h_result != null
+__global__ void __launch_bounds__(kThreads) k_sum_partials(const double* partials, int count, int nc, double* result, double* h_result) {
+  __shared__ double scratch[kWarps];
+  for (int c = 0; c < nc; ++c) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < count; i += kThreads) v += partials[(size_t)i * nc + c];
+    const double t = block_sum(v, scratch);
+    if (threadIdx.x == 0) {
+      if (result) result[c] = t;
+      if (h_result) h_result[c] = t;
+    }
+  }
+}
+
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale(T* x, int64_t n, T a) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) x[i] = mul(a, x[i]);
+}
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_axpy(T* y, T a, const T* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    T acc = y[i];
+    fmadd(acc, a, x[i]);
+    y[i] = acc;
+  }
+}
+
+// ==================================================================================================================
+// Host launchers
+// ==================================================================================================================
+namespace {
+
+constexpr size_t kSmemBudget = 100 * 1024;  // per CTA; two CTAs per SM stay resident
+
+inline int persistent_grid(llz_ctx_t ctx, int64_t work_items, int ctas_per_sm) {
+  int64_t g = (int64_t)ctx->num_sms * ctas_per_sm;
+  if (g > kMaxGrid) g = kMaxGrid;
+  if (g > work_items) g = work_items;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Rows one CTA covers per slab with VPT packets per thread.
+template <class T> constexpr int64_t slab_rows(int vpt) { return (int64_t)kThreads * vpt * Num<T>::VEC; }
+
+// VPT = 2 once there is enough work to fill the machine twice over, else 1 (keeps small problems spread over SMs).
+template <class T> inline int pick_vpt(llz_ctx_t ctx, int64_t n) {
+  return (n >= slab_rows<T>(2) * ctx->num_sms * 4) ? 2 : 1;
+}
+
+template <class F> inline int set_smem(F* kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  return LLZ_OK;
+}
+
+inline int check_launch(llz_ctx_t ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+  ctx->launches++;
+  return LLZ_OK;
+}
+
+}  // namespace
+
+template <class T> inline T from_double_host(const double a[2]);
+template <> inline float from_double_host<float>(const double a[2]) { return (float)a[0]; }
+template <> inline double from_double_host<double>(const double a[2]) { return a[0]; }
+template <> inline float2 from_double_host<float2>(const double a[2]) { return make_float2((float)a[0], (float)a[1]); }
+template <> inline double2 from_double_host<double2>(const double a[2]) { return make_double2(a[0], a[1]); }
+
+#define LLZ_DISPATCH(dtype, ...)                                               \
+  switch (dtype) {                                                             \
+    case LLZ_F32: { using T = float; __VA_ARGS__; } break;                     \
+    case LLZ_F64: { using T = double; __VA_ARGS__; } break;                    \
+    case LLZ_C64: { using T = float2; __VA_ARGS__; } break;                    \
+    case LLZ_C128: { using T = double2; __VA_ARGS__; } break;                  \
+    default: return fail(LLZ_ERR_INVALID, "unknown dtype %d", dtype);          \
+  }
+
+int max_project_cols(int dtype) {
+  const size_t per_col = (size_t)kWarps * dtype_nc(dtype) * sizeof(double);
+  return (int)((kSmemBudget - kWarps * sizeof(double)) / per_col);
+}
+int max_update_cols(int dtype) { return (int)(kSmemBudget / dtype_size(dtype)); }
+int max_combine_cols(int dtype, int nvec) {
+  (void)nvec;
+  return (int)(kSmemBudget / (dtype_size(dtype) * kMaxCombine));
+}
+
+template <class T, int VPT>
+static int project_impl(llz_ctx_t ctx, const ProjectArgs& a, int* grid_out) {
+  const size_t smem = ((size_t)kWarps * a.ncols * Num<T>::NC + kWarps) * sizeof(double);
+  LLZ_TRY(set_smem(k_project<T, VPT>, smem));
+  const int64_t nslabs = (a.n + slab_rows<T>(VPT) - 1) / slab_rows<T>(VPT);
+  const int grid = persistent_grid(ctx, nslabs, 2);
+  k_project<T, VPT><<<grid, kThreads, smem, ctx->stream>>>(a);
+  *grid_out = grid;
+  return check_launch(ctx, "k_project");
+}
+
+int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n,
+                   const Fold& fold, double* ph, int* grid_out) {
+  if (ncols < 0 || ncols > max_project_cols(dtype)) return fail(LLZ_ERR_INVALID, "project: %d columns per launch", ncols);
+  ProjectArgs a;
+  a.V = cs.V;
+  a.ld = cs.ld;
+  a.Q = cs.Q;
+  a.nq = cs.nq;
+  a.col0 = col0;
+  a.ncols = ncols;
+  a.w = w;
+  a.n = n;
+  a.fold = fold.mode;
+  a.pa = fold.alpha_partials;
+  a.npa = fold.n_partials;
+  a.beta_prev = fold.beta_prev;
+  a.alpha_out = fold.alpha_out;
+  a.ph = ph;
+  const size_t es = dtype_size(dtype);
+  a.u1 = cs.nv >= 1 ? (const char*)cs.V + (size_t)(cs.nv - 1) * cs.ld * es : nullptr;
+  a.u2 = cs.nv >= 2 ? (const char*)cs.V + (size_t)(cs.nv - 2) * cs.ld * es : nullptr;
+  if (a.fold >= 1 && !a.u1) return fail(LLZ_ERR_INVALID, "project: fold needs a previous basis column");
+  if (a.fold >= 2 && !a.u2) return fail(LLZ_ERR_INVALID, "project: fold=2 needs two previous basis columns");
+  LLZ_DISPATCH(dtype, {
+    if (pick_vpt<T>(ctx, n) == 2) return project_impl<T, 2>(ctx, a, grid_out);
+    return project_impl<T, 1>(ctx, a, grid_out);
+  });
+  return LLZ_OK;
+}
+
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, int j_alpha,
+                  const double* alpha, int j_beta, const double* beta_prev) {
+  const int nc = dtype_nc(dtype);
+  ReduceArgs a;
+  a.ph = ph;
+  a.grid = grid;
+  a.width = ncols * nc;
+  a.coef = coef + (size_t)col0 * nc;
+  a.i_alpha = (j_alpha >= col0 && j_alpha < col0 + ncols) ? (j_alpha - col0) * nc : -1;
+  a.alpha = alpha;
+  a.i_beta = (j_beta >= col0 && j_beta < col0 + ncols) ? (j_beta - col0) * nc : -1;
+  a.beta_prev = beta_prev;
+  if (a.width == 0) return LLZ_OK;
+  k_reduce<<<(a.width + 127) / 128, 128, 0, ctx->stream>>>(a);
+  return check_launch(ctx, "k_reduce");
+}
+
+template <class T, int VPT>
+static int update_impl(llz_ctx_t ctx, const UpdateArgs& a, int* grid_out) {
+  const size_t smem = std::max<size_t>(16, (size_t)a.ncols * sizeof(T));
+  LLZ_TRY(set_smem(k_update<T, VPT>, smem));
+  const int64_t nslabs = (a.n + slab_rows<T>(VPT) - 1) / slab_rows<T>(VPT);
+  const int grid = persistent_grid(ctx, nslabs, 2);
+  k_update<T, VPT><<<grid, kThreads, smem, ctx->stream>>>(a);
+  *grid_out = grid;
+  return check_launch(ctx, "k_update");
+}
+
+int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
+                  int64_t n, const double* coef, double* norm_partials, int* grid_out) {
+  if (ncols < 0 || ncols > max_update_cols(dtype)) return fail(LLZ_ERR_INVALID, "update: %d columns per launch", ncols);
+  UpdateArgs a;
+  a.V = cs.V;
+  a.ld = cs.ld;
+  a.Q = cs.Q;
+  a.nq = cs.nq;
+  a.col0 = col0;
+  a.ncols = ncols;
+  a.w = w;
+  a.out = out;
+  a.n = n;
+  a.coef = coef;
+  a.pb = norm_partials;
+  LLZ_DISPATCH(dtype, {
+    if (pick_vpt<T>(ctx, n) == 2) return update_impl<T, 2>(ctx, a, grid_out);
+    return update_impl<T, 1>(ctx, a, grid_out);
+  });
+  return LLZ_OK;
+}
+
+int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
+                         const ScalarSink& sink) {
+  ScaleNormArgs a;
+  a.x = x;
+  a.n = n;
+  a.pb = norm_partials;
+  a.npb = n_partials;
+  a.sink = sink;
+  LLZ_DISPATCH(dtype, {
+    const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
+    const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
+    k_scale_norm<T><<<grid, kThreads, 0, ctx->stream>>>(a);
+  });
+  return check_launch(ctx, "k_scale_norm");
+}
+
+int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, const void* u2, void* out, int64_t n,
+                      const Fold& fold, double* norm_partials, int* grid_out) {
+  RecurrenceArgs a;
+  a.w = w;
+  a.u1 = u1;
+  a.u2 = u2;
+  a.out = out;
+  a.n = n;
+  a.fold = fold.mode;
+  a.pa = fold.alpha_partials;
+  a.npa = fold.n_partials;
+  a.beta_prev = fold.beta_prev;
+  a.alpha_out = fold.alpha_out;
+  a.pb = norm_partials;
+  LLZ_DISPATCH(dtype, {
+    const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
+    const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
+    k_recurrence<T><<<grid, kThreads, 0, ctx->stream>>>(a);
+    *grid_out = grid;
+  });
+  return check_launch(ctx, "k_recurrence");
+}
+
+int launch_combine(llz_ctx_t ctx, int dtype, const void* V, int64_t ld, int col0, int ncols, const void* coef,
+                   int64_t ldc, int nvec, void* const* out, int64_t n, int accumulate, double* norm_partials,
+                   int* grid_out) {
+  if (nvec < 1 || nvec > kMaxCombine) return fail(LLZ_ERR_INVALID, "combine: nvec=%d", nvec);
+  if (ncols > max_combine_cols(dtype, nvec)) return fail(LLZ_ERR_INVALID, "combine: %d columns per launch", ncols);
+  CombineArgs a;
+  a.V = V;
+  a.ld = ld;
+  a.col0 = col0;
+  a.ncols = ncols;
+  a.coef = coef;
+  a.ldc = ldc;
+  a.nvec = nvec;
+  for (int r = 0; r < kMaxCombine; ++r) a.out[r] = r < nvec ? out[r] : nullptr;
+  a.n = n;
+  a.accumulate = accumulate;
+  a.pb = norm_partials;
+  LLZ_DISPATCH(dtype, {
+    const int64_t nslabs = (n + slab_rows<T>(1) - 1) / slab_rows<T>(1);
+    const int grid = persistent_grid(ctx, nslabs, 2);
+    if (nvec == 1) {
+      const size_t smem = std::max<size_t>(16, (size_t)ncols * sizeof(T));
+      LLZ_TRY(set_smem(k_combine<T, 1>, smem));
+      k_combine<T, 1><<<grid, kThreads, smem, ctx->stream>>>(a);
+    } else {
+      const size_t smem = std::max<size_t>(16, (size_t)ncols * sizeof(T) * kMaxCombine);
+      LLZ_TRY(set_smem(k_combine<T, kMaxCombine>, smem));
+      k_combine<T, kMaxCombine><<<grid, kThreads, smem, ctx->stream>>>(a);
+    }
+    *grid_out = grid;
+  });
+  return check_launch(ctx, "k_combine");
+}
+
+int launch_dot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out) {
+  LLZ_DISPATCH(dtype, {
+    const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
+    const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
+    k_dot<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)a, (const T*)b, n, partials);
+    *grid_out = grid;
+  });
+  return check_launch(ctx, "k_dot");
+}
+
+int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out) {
+  LLZ_DISPATCH(dtype, {
+    const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
+    const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
+    k_redot<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)a, (const T*)b, n, partials);
+    *grid_out = grid;
+  });
+  return check_launch(ctx, "k_redot");
+}
+
+int launch_sum_partials(llz_ctx_t ctx, const double* partials, int count, int nc, double* result, double* h_result) {
+  k_sum_partials<<<1, kThreads, 0, ctx->stream>>>(partials, count, nc, result, h_result);
+  return check_launch(ctx, "k_sum_partials");
+}
+
+int launch_scale(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double a[2]) {
+  LLZ_DISPATCH(dtype, {
+    const int grid = persistent_grid(ctx, (n + kThreads - 1) / kThreads, 8);
+    k_scale<T><<<grid, kThreads, 0, ctx->stream>>>((T*)x, n, from_double_host<T>(a));
+  });
+  return check_launch(ctx, "k_scale");
+}
+
+int launch_axpy(llz_ctx_t ctx, int dtype, void* y, const double a[2], const void* x, int64_t n) {
+  LLZ_DISPATCH(dtype, {
+    const int grid = persistent_grid(ctx, (n + kThreads - 1) / kThreads, 8);
+    k_axpy<T><<<grid, kThreads, 0, ctx->stream>>>((T*)y, from_double_host<T>(a), (const T*)x, n);
+  });
+  return check_launch(ctx, "k_axpy");
+}
+
+}  // namespace llz

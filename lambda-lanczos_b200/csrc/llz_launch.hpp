@@ -1,0 +1,71 @@
+// llz_launch.hpp — typed-erased launchers of the streaming kernels (llz_kernels.cu).  All launch on ctx->stream.
+#pragma once
+#include "llz_internal.hpp"
+
+namespace llz {
+
+// The set of orthonormal columns a vector is projected on: `nq` separately allocated vectors (device pointer table)
+// followed by `nv` contiguous columns of the Krylov basis.  Column index space: [0,nq) = Q, [nq,nq+nv) = V.
+struct ColumnSet {
+  const void* V = nullptr;
+  int64_t ld = 0;  // elements between consecutive basis columns
+  int nv = 0;
+  const void* const* Q = nullptr;  // device array of nq device pointers
+  int nq = 0;
+  int ncols() const { return nq + nv; }
+};
+
+// Folding of the three-term recurrence into the projection / update (lambda_lanczos.hpp:251-257):
+//   w' = w - alpha u_{k-1} - beta_{k-2} u_{k-2},  alpha = sum(alpha_partials)
+struct Fold {
+  int mode = 0;                         // 0: none, 1: alpha only (first iteration), 2: alpha and beta
+  const double* alpha_partials = nullptr;
+  int n_partials = 0;
+  const double* beta_prev = nullptr;    // device address of beta_{k-2}
+  double* alpha_out = nullptr;          // device address receiving alpha_{k-1}
+};
+
+// Where scale_by_norm publishes the iteration's scalars.
+struct ScalarSink {
+  double* beta_out = nullptr;     // device bank slot for beta_{k-1} (may be null)
+  const double* alpha_in = nullptr;  // device bank slot of alpha_{k-1} (copied to the host mirror)
+  double* h_alpha = nullptr;      // mapped pinned host slots (may be null)
+  double* h_beta = nullptr;
+  long long* h_flag = nullptr;    // mapped pinned: set to `flag_value` after the scalars are visible
+  long long flag_value = 0;
+};
+
+int max_project_cols(int dtype);  // columns one projection launch can accumulate in shared memory
+int max_update_cols(int dtype);
+int max_combine_cols(int dtype, int nvec);
+
+// h partials: ph[cta][ncols*NC] for the column chunk [col0, col0+ncols); returns the grid used.
+int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n,
+                   const Fold& fold, double* ph, int* grid_out);
+// coef[(col0+j)*NC+c] = sum_cta ph[cta][j*NC+c]  (+alpha at column j_alpha, +beta_prev at j_beta; -1 = none)
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, int j_alpha,
+                  const double* alpha, int j_beta, const double* beta_prev);
+// out = w - sum_j coef_j col_j over the chunk; if norm_partials != null, per-CTA partials of ||out||^2.
+int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
+                  int64_t n, const double* coef, double* norm_partials, int* grid_out);
+// x *= 1/sqrt(sum partials); publishes beta (and alpha) per `sink`.  Leaves x untouched when the norm is not > 0.
+int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
+                         const ScalarSink& sink);
+// out = w - alpha u1 - beta u2 (no reorthogonalisation; exponentiator.hpp:112-118) + norm partials
+int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, const void* u2, void* out, int64_t n,
+                      const Fold& fold, double* norm_partials, int* grid_out);
+// out_r (+)= sum_j coef[r*ldc + j] col_j for r < nvec (<= 5); coef is a DEVICE array of T; norm partials per vector
+// at norm_partials[r*kMaxGrid + cta] when non-null.
+int launch_combine(llz_ctx_t ctx, int dtype, const void* V, int64_t ld, int col0, int ncols, const void* coef,
+                   int64_t ldc, int nvec, void* const* out /* host array of device pointers */, int64_t n,
+                   int accumulate, double* norm_partials, int* grid_out);
+// partials of <a,b> (NC doubles per CTA, interleaved) and of Re<a,b> only
+int launch_dot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out);
+// partials of Re<a,b> only, one double per CTA (alpha when the operator cannot fuse the dot)
+int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out);
+// result[0..NC) = sum of partials (single CTA)
+int launch_sum_partials(llz_ctx_t ctx, const double* partials, int count, int nc, double* result, double* h_result);
+int launch_scale(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double a[2]);
+int launch_axpy(llz_ctx_t ctx, int dtype, void* y, const double a[2], const void* x, int64_t n);
+
+}  // namespace llz

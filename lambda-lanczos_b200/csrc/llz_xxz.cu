@@ -1,0 +1,195 @@
+// llz_xxz.cu — matrix-free spin-1/2 XXZ chain operator in a fixed-Sz sector (BASELINE.json configs 4 and 5):
+//     H = sum_<i,i+1> [ Jxy/2 (S+_i S-_{i+1} + h.c.) + Jz Sz_i Sz_{i+1} ]
+// on L sites, basis = all L-bit integers with n_up set bits in increasing order.  Nothing of the matrix is stored:
+// y_r = diag(s_r) x_r + Jxy/2 * sum_{anti-parallel bonds b of s_r} x[rank(s_r ^ flip_b)]   (H is symmetric, so the
+// gather form needs no atomics).  rank() is the combinatorial number system evaluated with two Lin tables (low / high
+// half of the bit string, 2^(L/2) entries each — they live in L1/L2); each thread unranks the first of ITEMS
+// consecutive states once and steps to the next ones with Gosper's bit trick.
+// The alpha = Re<x, Hx> dot is fused into the epilogue like the CSR kernel's.
+#include <algorithm>
+#include <vector>
+
+#include "llz_device.cuh"
+#include "llz_launch.hpp"
+
+namespace llz {
+
+__constant__ unsigned long long c_binom[34][34];
+
+struct XxzParams {
+  int L, n_up, half;   // half = number of low bits covered by the low table
+  int periodic;
+  double jz4, jxy2;    // Jz/4, Jxy/2
+  const uint32_t* rank_lo;  // [2^half]
+  const uint32_t* rank_hi;  // [2^(L-half)]
+  int64_t n;
+  int64_t row0;        // first local row (row-sharded runs)
+};
+
+__device__ __forceinline__ uint32_t xxz_unrank(int64_t idx, int L, int n_up) {
+  uint32_t s = 0;
+  int p = L - 1;
+  unsigned long long rem = (unsigned long long)idx;
+  for (int k = n_up; k >= 1; --k) {
+    while (c_binom[p][k] > rem) --p;
+    s |= (1u << p);
+    rem -= c_binom[p][k];
+    --p;
+  }
+  return s;
+}
+
+__device__ __forceinline__ uint32_t gosper_next(uint32_t s) {
+  const uint32_t t = s | (s - 1);
+  return (t + 1) | (((~t & -~t) - 1) >> __ffs(s));
+}
+
+template <class T, int ITEMS>
+__global__ void __launch_bounds__(kThreads, 4)
+    k_xxz_apply(const T* __restrict__ x, T* __restrict__ y, XxzParams p, typename Num<T>::R sigma, double* pa) {
+  using R = typename Num<T>::R;
+  __shared__ double scratch[kWarps];
+  const uint32_t mask = (p.L >= 32) ? 0xffffffffu : ((1u << p.L) - 1u);
+  const uint32_t lo_mask = (1u << p.half) - 1u;
+  const uint32_t wrap_flip = (1u << (p.L - 1)) | 1u;
+  const int nbonds = p.periodic ? p.L : p.L - 1;
+  double dot = 0.0;
+  const int64_t chunk = (int64_t)kThreads * ITEMS;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < p.n; base += (int64_t)gridDim.x * chunk) {
+    const int64_t first = base + (int64_t)threadIdx.x * ITEMS;
+    if (first >= p.n) continue;
+    uint32_t s = xxz_unrank(p.row0 + first, p.L, p.n_up);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int64_t r = first + it;
+      if (r >= p.n) break;
+      // anti-parallel bonds: bit i set <=> sites i and i+1 differ (bit L-1 = wrap bond under periodic boundaries)
+      uint32_t d = (s ^ (s >> 1)) & (mask >> 1);
+      if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) d |= (1u << (p.L - 1));
+      const int anti = __popc(d);
+      const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
+      T acc = zero_of(T());
+      while (d) {
+        const int i = __ffs(d) - 1;
+        d &= d - 1;
+        const uint32_t t = s ^ ((i == p.L - 1) ? wrap_flip : (3u << i));
+        const int64_t j = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half)) - p.row0;
+        const T xv = __ldg(x + j);
+        acc = add_t(acc, xv);
+      }
+      const T xi = x[r];
+      T yi = scale_real(acc, (R)p.jxy2);
+      yi = add_t(yi, scale_real(xi, diag + sigma));
+      y[r] = yi;
+      dot += re_conj_mul(xi, yi);
+      s = gosper_next(s);
+    }
+  }
+  const double t = block_sum(dot, scratch);
+  if (threadIdx.x == 0) pa[blockIdx.x] = t;
+}
+
+struct XxzOpBase : OpBase {
+  XxzParams prm;
+  uint32_t* d_lo = nullptr;
+  uint32_t* d_hi = nullptr;
+  ~XxzOpBase() override {
+    if (d_lo) cudaFree(d_lo);
+    if (d_hi) cudaFree(d_hi);
+  }
+};
+
+template <class T> struct XxzOp : XxzOpBase {
+  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa) override {
+    constexpr int ITEMS = 4;
+    const int64_t chunk = (int64_t)kThreads * ITEMS;
+    int64_t g = std::min<int64_t>((n_local + chunk - 1) / chunk, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
+    if (g < 1) g = 1;
+    k_xxz_apply<T, ITEMS><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, prm, (typename Num<T>::R)sigma, pa);
+    *npa = (int)g;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_apply: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return LLZ_OK;
+  }
+};
+
+static unsigned long long host_binom[34][34];
+static bool binom_ready = false;
+static void init_binom() {
+  if (binom_ready) return;
+  for (int n = 0; n < 34; ++n) {
+    for (int k = 0; k < 34; ++k) host_binom[n][k] = 0;
+    host_binom[n][0] = 1;
+    for (int k = 1; k <= n; ++k) host_binom[n][k] = host_binom[n - 1][k - 1] + (k <= n - 1 ? host_binom[n - 1][k] : 0);
+  }
+  binom_ready = true;
+}
+
+}  // namespace llz
+
+using namespace llz;
+
+extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, double jz, double jxy, int periodic, llz_op_t* out) {
+  if (!ctx || !out || L < 2 || L > 32 || n_up < 0 || n_up > L || dtype_size(dtype) == 0)
+    return fail(LLZ_ERR_INVALID, "op_create_xxz: need 2 <= L <= 32, 0 <= n_up <= L");
+  if (ctx->nranks > 1) return fail(LLZ_ERR_UNSUPPORTED, "row-sharded XXZ is not built yet");
+  LLZ_CUDA(cudaSetDevice(ctx->device));
+  init_binom();
+  LLZ_CUDA(cudaMemcpyToSymbol(c_binom, host_binom, sizeof(host_binom)));
+  XxzOpBase* op = nullptr;
+  switch (dtype) {
+    case LLZ_F32: op = new XxzOp<float>(); break;
+    case LLZ_F64: op = new XxzOp<double>(); break;
+    case LLZ_C64: op = new XxzOp<float2>(); break;
+    case LLZ_C128: op = new XxzOp<double2>(); break;
+  }
+  op->ctx = ctx;
+  op->dtype = dtype;
+  op->n_local = (int64_t)host_binom[L][n_up];
+  op->bytes = 0;
+  const int half = L / 2;
+  // Lin tables: rank(s) = lo[s & lo_mask] + hi[s >> half].  The j-th set bit (1-based, counted from bit 0) at
+  // position q contributes C(q, j); for the high half j continues from the number of set bits in the low half,
+  // which the fixed magnetisation determines: popcount(low) = n_up - popcount(high).
+  std::vector<uint32_t> lo((size_t)1 << half), hi((size_t)1 << (L - half));
+  for (uint32_t b = 0; b < lo.size(); ++b) {
+    unsigned long long r = 0;
+    int j = 0;
+    for (int q = 0; q < half; ++q)
+      if (b >> q & 1u) r += host_binom[q][++j];
+    lo[b] = (uint32_t)r;
+  }
+  for (uint32_t b = 0; b < hi.size(); ++b) {
+    const int pc = __builtin_popcount(b);
+    unsigned long long r = 0;
+    if (pc <= n_up) {
+      int j = n_up - pc;
+      for (int q = 0; q < L - half; ++q)
+        if (b >> q & 1u) r += host_binom[q + half][++j];
+    }
+    hi[b] = (uint32_t)r;
+  }
+  cudaError_t e = cudaMalloc(&op->d_lo, lo.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&op->d_hi, hi.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_lo, lo.data(), lo.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_hi, hi.data(), hi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete op;
+    return fail(LLZ_ERR_CUDA, "op_create_xxz: %s", cudaGetErrorString(e));
+  }
+  op->prm.L = L;
+  op->prm.n_up = n_up;
+  op->prm.half = half;
+  op->prm.periodic = periodic ? 1 : 0;
+  op->prm.jz4 = jz * 0.25;
+  op->prm.jxy2 = jxy * 0.5;
+  op->prm.rank_lo = op->d_lo;
+  op->prm.rank_hi = op->d_hi;
+  op->prm.n = op->n_local;
+  op->prm.row0 = 0;
+  llz_op_t h = new llz_op_s();
+  h->impl = op;
+  *out = h;
+  return LLZ_OK;
+}

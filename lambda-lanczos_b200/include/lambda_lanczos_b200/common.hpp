@@ -1,0 +1,125 @@
+// common.hpp — type utilities and RAII wrappers over the C ABI (include/llz.h) shared by the host-side engine headers.
+// Header-only C++14; needs -I<repo>/include for llz.h and linking against libllz.so.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "llz.h"
+
+namespace lambda_lanczos_b200 {
+namespace util {
+
+// real_t<T>: T for real types, the component type for std::complex (reference: util/common.hpp:80-102)
+template <typename T> struct realTypeMap { typedef T type; };
+template <typename T> struct realTypeMap<std::complex<T>> { typedef T type; };
+template <typename T> using real_t = typename realTypeMap<T>::type;
+
+// conjugate that is the identity on real types (reference: util/common.hpp:112-134)
+template <typename T> inline T typed_conj(const T& v) { return v; }
+template <typename T> inline std::complex<T> typed_conj(const std::complex<T>& v) { return std::conj(v); }
+
+template <typename T> struct dtype_of;
+template <> struct dtype_of<float> { static constexpr int value = LLZ_F32; };
+template <> struct dtype_of<double> { static constexpr int value = LLZ_F64; };
+template <> struct dtype_of<std::complex<float>> { static constexpr int value = LLZ_C64; };
+template <> struct dtype_of<std::complex<double>> { static constexpr int value = LLZ_C128; };
+
+template <typename T> inline void to_pair(const T& v, double out[2]) {
+  out[0] = static_cast<double>(v);
+  out[1] = 0.0;
+}
+template <typename T> inline void to_pair(const std::complex<T>& v, double out[2]) {
+  out[0] = static_cast<double>(v.real());
+  out[1] = static_cast<double>(v.imag());
+}
+
+}  // namespace util
+
+// The reference reports nothing but asserts; the C ABI returns status codes and this layer turns a
+// non-zero status into an exception.
+class Error : public std::runtime_error {
+ public:
+  Error(int status, const std::string& what) : std::runtime_error(what), status_(status) {}
+  int status() const { return status_; }
+
+ private:
+  int status_;
+};
+
+inline void check(int status, const char* where) {
+  if (status != LLZ_OK)
+    throw Error(status, std::string(where) + ": " + llz_status_string(status) + " — " + llz_last_error());
+}
+
+// One GPU + one stream (+ one rank of a row-sharded group).
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    llz_ctx_t c = nullptr;
+    check(llz_ctx_create(device, &c), "llz_ctx_create");
+    h_.reset(c, [](llz_ctx_t p) { llz_ctx_destroy(p); });
+  }
+  // Non-owning view of a context created through the C ABI.
+  static Context borrow(llz_ctx_t c) {
+    Context x(Borrow{});
+    x.h_.reset(c, [](llz_ctx_t) {});
+    return x;
+  }
+  // An empty handle (no device attached); only useful as a placeholder.
+  static Context none() { return Context(Borrow{}); }
+  llz_ctx_t get() const { return h_.get(); }
+  void synchronize() const { check(llz_ctx_synchronize(h_.get()), "llz_ctx_synchronize"); }
+  uint64_t launch_count() const {
+    uint64_t c = 0;
+    check(llz_ctx_launch_count(h_.get(), &c), "llz_ctx_launch_count");
+    return c;
+  }
+  // Process-wide default context on device 0, created on first use.
+  static Context& default_context() {
+    static Context ctx(0);
+    return ctx;
+  }
+
+ private:
+  struct Borrow {};
+  explicit Context(Borrow) {}
+  std::shared_ptr<llz_ctx_s> h_;
+};
+
+// Device vector of n_local elements of T.
+template <typename T>
+class DeviceVector {
+ public:
+  DeviceVector() {}
+  DeviceVector(const Context& ctx, size_t n) : n_(n) {
+    llz_vec_t v = nullptr;
+    check(llz_vec_create(ctx.get(), util::dtype_of<T>::value, (int64_t)n, &v), "llz_vec_create");
+    h_.reset(v, [](llz_vec_t p) { llz_vec_destroy(p); });
+  }
+  bool valid() const { return (bool)h_; }
+  size_t size() const { return n_; }
+  llz_vec_t get() const { return h_.get(); }
+  T* device_ptr() const {
+    void* p = nullptr;
+    check(llz_vec_device_ptr(h_.get(), &p), "llz_vec_device_ptr");
+    return static_cast<T*>(p);
+  }
+  void upload(const T* host) { check(llz_vec_upload(h_.get(), host), "llz_vec_upload"); }
+  void upload(const std::vector<T>& host) { upload(host.data()); }
+  void download(T* host) const { check(llz_vec_download(h_.get(), host), "llz_vec_download"); }
+  std::vector<T> to_host() const {
+    std::vector<T> out(n_);
+    download(out.data());
+    return out;
+  }
+
+ private:
+  std::shared_ptr<llz_vec_s> h_;
+  size_t n_ = 0;
+};
+
+}  // namespace lambda_lanczos_b200

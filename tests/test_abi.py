@@ -1,0 +1,75 @@
+"""CPU tests of the drop-in boundary: libllz.so builds, loads, exports every symbol include/llz.h declares, refuses to
+run without a GPU, and the product never reaches for the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "llz.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(llz_[a-z0-9_]+)\s*\(", text)) - {"llz_apply_fn"})
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    for must in ("llz_ctx_create", "llz_op_create_csr", "llz_op_create_xxz", "llz_op_create_callback", "llz_vec_dot",
+                 "llz_vec_schmidt_orth", "llz_krylov_step", "llz_krylov_combine", "llz_eigs_run", "llz_expm_run"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.lib()
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.llz_version() == 100
+
+
+def test_status_strings(pkg):
+    lib = pkg.lib()
+    assert lib.llz_status_string(0) == b"ok"
+    assert b"CPU" in lib.llz_status_string(6)
+
+
+def test_no_cpu_fallback_without_device(pkg):
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.LlzError) as e:
+        pkg.Context(0)
+    assert e.value.status == 6  # LLZ_ERR_NO_DEVICE
+
+
+def test_bad_arguments_are_reported_not_crashed(pkg):
+    lib = pkg.lib()
+    assert lib.llz_ctx_destroy(None) == 0
+    assert lib.llz_vec_destroy(None) == 0
+    assert lib.llz_op_destroy(None) == 0
+    out = C.c_void_p()
+    assert lib.llz_vec_create(None, 1, C.c_int64(4), C.byref(out)) == 1  # LLZ_ERR_INVALID
+    assert lib.llz_krylov_create(None, 1, C.c_int64(4), C.c_int64(4), C.byref(out)) == 1
+    assert b"bad argument" in lib.llz_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    pkg_dir = os.path.join(ROOT, "lambda-lanczos_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg_dir):
+        if "build" in base.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"import\s+oracle|from\s+oracle|oracle/|llzo_|libllz_ref|libllz_oracle|dlopen", text):
+                    offenders.append(os.path.join(base, f))
+    assert not offenders, offenders
