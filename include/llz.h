@@ -160,8 +160,14 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
  *   beta_{k-1} = ||u_k||; u_k /= beta_{k-1}                                  (:262,285, exponentiator.hpp:145,160)
  * Asynchronous: returns once the work is queued; the scalars arrive through llz_krylov_fetch. */
 int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth);
-/* Block until iteration k (1-based) has finished and return alpha_{k-1}, beta_{k-1}. */
-int llz_krylov_fetch(llz_krylov_t kry, int64_t k, double* alpha, double* beta);
+/* Block until iteration k (1-based) has finished and return alpha_{k-1}, beta_{k-1} and ||w'||, the norm of the new
+ * vector after the three-term recurrence but BEFORE the Gram-Schmidt pass (= beta for LLZ_ORTH_RECURRENCE).
+ * beta << ||w'|| means the pass cancelled most of the vector and one pass was not enough (DGKS criterion). */
+int llz_krylov_fetch(llz_krylov_t kry, int64_t k, double* alpha, double* beta, double* wnorm);
+/* Repeat the Gram-Schmidt pass on the (normalised) vector of iteration k and renormalise it; beta_{k-1} is multiplied
+ * by the shrink factor returned in *shrink.  Iterations already enqueued beyond k are discarded (steps() == k
+ * afterwards).  Synchronous; meant for the rare near-breakdown iterations. */
+int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink);
 /* Number of iterations enqueued so far (stored columns = this + 1). */
 int llz_krylov_steps(llz_krylov_t kry, int64_t* k);
 /* out_r = sum_{j<m} coeff[r*m + j] u_j for r < nvec, optionally normalised — the eigenvector assembly of

@@ -269,10 +269,15 @@ class Krylov:
     def step(self, op: Operator, sigma: float = 0.0, orth: int = ORTH_FULL):
         _check(lib().llz_krylov_step(self.h, op.h, C.c_double(sigma), C.c_int(orth)), "llz_krylov_step")
 
-    def fetch(self, k: int):
-        a, b = C.c_double(0), C.c_double(0)
-        _check(lib().llz_krylov_fetch(self.h, i64(k), C.byref(a), C.byref(b)), "llz_krylov_fetch")
-        return float(a.value), float(b.value)
+    def fetch(self, k: int, with_wnorm: bool = False):
+        a, b, w = C.c_double(0), C.c_double(0), C.c_double(0)
+        _check(lib().llz_krylov_fetch(self.h, i64(k), C.byref(a), C.byref(b), C.byref(w)), "llz_krylov_fetch")
+        return (float(a.value), float(b.value), float(w.value)) if with_wnorm else (float(a.value), float(b.value))
+
+    def refine(self, k: int) -> float:
+        s = C.c_double(0)
+        _check(lib().llz_krylov_refine(self.h, i64(k), C.byref(s)), "llz_krylov_refine")
+        return float(s.value)
 
     def column(self, j: int) -> np.ndarray:
         out = np.empty(self.n, dtype=self.dtype)

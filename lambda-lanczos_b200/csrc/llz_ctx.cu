@@ -285,7 +285,7 @@ int llz_vec_schmidt_orth(llz_vec_t w, const llz_vec_t* basis, int64_t count, int
   LLZ_CUDA(cudaMemcpyAsync(ctx->d_ptrs, ptrs.data(), sizeof(void*) * count, cudaMemcpyHostToDevice, ctx->stream));
   LLZ_CUDA(cudaStreamSynchronize(ctx->stream));  // ptrs is a stack-lifetime staging buffer
   const int chunk = max_project_cols(w->dtype);
-  const size_t need = (size_t)kMaxGrid * (size_t)(count < chunk ? count : chunk) * nc;
+  const size_t need = (size_t)kMaxGrid * ((size_t)(count < chunk ? count : chunk) * nc + 1);
   if (need > ctx->ph_capacity) {
     if (ctx->d_ph) cudaFree(ctx->d_ph);
     ctx->d_ph = nullptr;
@@ -301,7 +301,7 @@ int llz_vec_schmidt_orth(llz_vec_t w, const llz_vec_t* basis, int64_t count, int
       const int nc_cols = (int)((count - c0) < chunk ? (count - c0) : chunk);
       int grid = 0;
       LLZ_TRY(launch_project(ctx, w->dtype, cs, c0, nc_cols, w->d, w->n, nofold, ctx->d_ph, &grid));
-      LLZ_TRY(launch_reduce(ctx, w->dtype, ctx->d_ph, grid, c0, nc_cols, ctx->d_coef, -1, nullptr, -1, nullptr));
+      LLZ_TRY(launch_reduce(ctx, w->dtype, ctx->d_ph, grid, c0, nc_cols, ctx->d_coef, -1, nullptr, -1, nullptr, nullptr));
     }
     LLZ_TRY(comm_allreduce_sum(ctx, ctx->d_coef, (int)count * nc));
     const int uchunk = max_update_cols(w->dtype);

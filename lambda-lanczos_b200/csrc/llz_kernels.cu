@@ -47,7 +47,7 @@ template <class T> __device__ __forceinline__ const T* column_ptr(const void* V,
 
 template <class T, int VPT, bool FULL>
 __device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base, typename Num<T>::R alpha,
-                                             typename Num<T>::R beta, double* hs_warp, int lane) {
+                                             typename Num<T>::R beta, double* hs_warp, int lane, double& wnorm2) {
   using R = typename Num<T>::R;
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC, M = CT * NC;
   const int tid = threadIdx.x;
@@ -79,6 +79,11 @@ __device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base,
       }
     }
   }
+
+#pragma unroll
+  for (int i = 0; i < VPT; ++i)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) wnorm2 += abs2(wp[i].e[e]);  // ||w'||^2: the DGKS cancellation test needs it
 
   for (int j0 = 0; j0 < a.ncols; j0 += CT) {
     T acc[CT];
@@ -148,28 +153,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
   constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
   const int64_t nslabs = (a.n + SLAB - 1) / SLAB;
   double* hs_warp = hs + warp * width;
+  double wnorm2 = 0.0;
   for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
     const int64_t base = s * SLAB;
     if (base + SLAB <= a.n)
-      project_slab<T, VPT, true>(a, base, alpha, beta, hs_warp, lane);
+      project_slab<T, VPT, true>(a, base, alpha, beta, hs_warp, lane, wnorm2);
     else
-      project_slab<T, VPT, false>(a, base, alpha, beta, hs_warp, lane);
+      project_slab<T, VPT, false>(a, base, alpha, beta, hs_warp, lane, wnorm2);
   }
-  __syncthreads();
-  double* out = a.ph + (size_t)blockIdx.x * width;
+  const double wn = block_sum(wnorm2, scratch);  // also orders the hs writes before the cross-warp sum below
+  double* out = a.ph + (size_t)blockIdx.x * (width + 1);
   for (int i = tid; i < width; i += kThreads) {
     double s = 0.0;
 #pragma unroll
     for (int wi = 0; wi < kWarps; ++wi) s += hs[wi * width + i];
     out[i] = s;
   }
+  if (tid == 0) out[width] = wn;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 struct ReduceArgs {
   const double* ph;
   int grid;
-  int width;  // ncols*NC of the chunk
+  double* wnorm2;  // receives sum of the extra ||w'||^2 slot (may be null)
+  int width;  // ncols*NC of the chunk; each CTA row of ph holds width + 1 doubles
   double* coef;  // already offset to the chunk
   int i_alpha;   // index (in doubles, within the chunk) receiving +alpha, or -1
   const double* alpha;
@@ -179,9 +187,13 @@ struct ReduceArgs {
 
 __global__ void __launch_bounds__(128) k_reduce(ReduceArgs a) {
   const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= a.width) return;
+  if (i > a.width) return;
   double s = 0.0;
-  for (int c = 0; c < a.grid; ++c) s += a.ph[(size_t)c * a.width + i];
+  for (int c = 0; c < a.grid; ++c) s += a.ph[(size_t)c * (a.width + 1) + i];
+  if (i == a.width) {
+    if (a.wnorm2) *a.wnorm2 = s;
+    return;
+  }
   if (i == a.i_alpha) s += *a.alpha;
   if (i == a.i_beta) s += *a.beta_prev;
   a.coef[i] = s;
@@ -304,6 +316,7 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(S
     if (a.sink.beta_out) *a.sink.beta_out = beta;
     if (a.sink.h_beta) *a.sink.h_beta = beta;
     if (a.sink.h_alpha && a.sink.alpha_in) *a.sink.h_alpha = *a.sink.alpha_in;
+    if (a.sink.h_wnorm) *a.sink.h_wnorm = a.sink.wnorm2_in ? sqrt(*a.sink.wnorm2_in) : beta;
     if (a.sink.h_flag) {
       __threadfence_system();
       *reinterpret_cast<volatile long long*>(a.sink.h_flag) = a.sink.flag_value;
@@ -670,19 +683,19 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
 }
 
 int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, int j_alpha,
-                  const double* alpha, int j_beta, const double* beta_prev) {
+                  const double* alpha, int j_beta, const double* beta_prev, double* wnorm2) {
   const int nc = dtype_nc(dtype);
   ReduceArgs a;
   a.ph = ph;
   a.grid = grid;
+  a.wnorm2 = wnorm2;
   a.width = ncols * nc;
   a.coef = coef + (size_t)col0 * nc;
   a.i_alpha = (j_alpha >= col0 && j_alpha < col0 + ncols) ? (j_alpha - col0) * nc : -1;
   a.alpha = alpha;
   a.i_beta = (j_beta >= col0 && j_beta < col0 + ncols) ? (j_beta - col0) * nc : -1;
   a.beta_prev = beta_prev;
-  if (a.width == 0) return LLZ_OK;
-  k_reduce<<<(a.width + 127) / 128, 128, 0, ctx->stream>>>(a);
+  k_reduce<<<(a.width + 1 + 127) / 128, 128, 0, ctx->stream>>>(a);
   return check_launch(ctx, "k_reduce");
 }
 

@@ -84,6 +84,7 @@ struct llz_krylov_s {
   double* h_alpha = nullptr;  // pinned + mapped
   double* h_beta = nullptr;
   double* h_misc = nullptr;
+  double* h_wnorm = nullptr;  // ||w'|| before the Gram-Schmidt pass of each iteration (DGKS cancellation test)
   long long* h_flag = nullptr;
   int64_t scalar_cap = 0;
   // locked vectors
@@ -165,7 +166,7 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, i
     const int pchunk = max_project_cols(kry->dtype);
     for (int c0 = 0; c0 < total; c0 += pchunk) {
       const int cols = std::min(pchunk, total - c0);
-      LLZ_TRY(ensure_ph(kry, (size_t)max_grid * (size_t)cols * nc));
+      LLZ_TRY(ensure_ph(kry, (size_t)max_grid * ((size_t)cols * nc + 1)));
       int grid = 0;
       {
         ProfScope ps(ctx, "project", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + 1 + fold.mode));
@@ -176,10 +177,12 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, i
         const bool add = ctx->rank == 0;
         ProfScope ps(ctx, "reduce", 0.0);
         LLZ_TRY(launch_reduce(ctx, kry->dtype, kry->d_ph, grid, c0, cols, kry->d_coef, add ? j_alpha : -1,
-                              fold.alpha_out, add ? j_beta : -1, fold.beta_prev));
+                              fold.alpha_out, add ? j_beta : -1, fold.beta_prev,
+                              (c0 + cols >= total) ? kry->d_misc + 1 : nullptr));
       }
     }
     LLZ_TRY(comm_allreduce_sum(ctx, kry->d_coef, total * nc));
+    LLZ_TRY(comm_allreduce_sum(ctx, kry->d_misc + 1, 1));
   }
   const int uchunk = max_update_cols(kry->dtype);
   int c0 = 0;
@@ -271,6 +274,7 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
   LLZ_CUDA(cudaHostAlloc(&kry->h_alpha, sc * sizeof(double), cudaHostAllocMapped));
   LLZ_CUDA(cudaHostAlloc(&kry->h_beta, sc * sizeof(double), cudaHostAllocMapped));
   LLZ_CUDA(cudaHostAlloc(&kry->h_misc, 8 * sizeof(double), cudaHostAllocMapped));
+  LLZ_CUDA(cudaHostAlloc(&kry->h_wnorm, sc * sizeof(double), cudaHostAllocMapped));
   LLZ_CUDA(cudaHostAlloc(&kry->h_flag, sizeof(long long) * 2, cudaHostAllocMapped));
   kry->h_flag[0] = 0;
   int s = ensure_cols(kry, 2);
@@ -311,6 +315,7 @@ int llz_krylov_destroy(llz_krylov_t kry) {
   cudaFreeHost(kry->h_alpha);
   cudaFreeHost(kry->h_beta);
   cudaFreeHost(kry->h_misc);
+  cudaFreeHost(kry->h_wnorm);
   cudaFreeHost(kry->h_flag);
   delete kry;
   return LLZ_OK;
@@ -371,6 +376,8 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   cs.nq = kry->nq;
   Fold nofold;
   int grid = 0;
+  // the start vector may lie almost inside span(locked): orthogonalise twice ("twice is enough")
+  if (kry->nq > 0) LLZ_TRY(cgs_pass(kry, cs, u0, nofold, -1, -1, false, &grid));
   LLZ_TRY(cgs_pass(kry, cs, u0, nofold, -1, -1, true, &grid));
   LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
   ScalarSink sink;
@@ -440,6 +447,8 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
   sink.alpha_in = kry->d_alpha + (k - 1);
   sink.h_alpha = kry->h_alpha + (k - 1);
   sink.h_beta = kry->h_beta + (k - 1);
+  sink.h_wnorm = kry->h_wnorm + (k - 1);
+  sink.wnorm2_in = (orth == LLZ_ORTH_RECURRENCE) ? nullptr : kry->d_misc + 1;
   sink.h_flag = kry->h_flag;
   sink.flag_value = k;
   {
@@ -450,7 +459,7 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
   return LLZ_OK;
 }
 
-int llz_krylov_fetch(llz_krylov_t kry, int64_t k, double* alpha, double* beta) {
+int llz_krylov_fetch(llz_krylov_t kry, int64_t k, double* alpha, double* beta, double* wnorm) {
   if (!kry || k < 1 || k > kry->k) return fail(LLZ_ERR_INVALID, "krylov_fetch: iteration %lld not enqueued", (long long)k);
   volatile long long* flag = kry->h_flag;
   uint64_t spins = 0;
@@ -470,6 +479,40 @@ int llz_krylov_fetch(llz_krylov_t kry, int64_t k, double* alpha, double* beta) {
   __sync_synchronize();
   if (alpha) *alpha = ((volatile double*)kry->h_alpha)[k - 1];
   if (beta) *beta = ((volatile double*)kry->h_beta)[k - 1];
+  if (wnorm) *wnorm = ((volatile double*)kry->h_wnorm)[k - 1];
+  return LLZ_OK;
+}
+
+int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink) {
+  if (!kry || k < 1 || k > kry->k) return fail(LLZ_ERR_INVALID, "krylov_refine: iteration %lld not enqueued", (long long)k);
+  llz_ctx_t ctx = kry->ctx;
+  void* y = kry->col(k);
+  ColumnSet cs;
+  cs.V = kry->col(0);
+  cs.ld = kry->ld;
+  cs.nv = (int)k;
+  cs.Q = (const void* const*)kry->d_qptrs;
+  cs.nq = kry->nq;
+  Fold nofold;
+  int grid = 0;
+  LLZ_TRY(cgs_pass(kry, cs, y, nofold, -1, -1, true, &grid));
+  LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
+  ScalarSink sink;
+  sink.beta_out = kry->d_misc;
+  sink.h_beta = kry->h_misc;
+  {
+    ProfScope ps(ctx, "scale", (double)kry->n * (double)dtype_size(kry->dtype) * 2);
+    LLZ_TRY(launch_scale_by_norm(ctx, kry->dtype, y, kry->n, kry->d_pb, grid, sink));
+  }
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));  // also drains the speculative iterations queued after k
+  const double nu = kry->h_misc[0];              // column k had unit norm: nu is the shrink factor of this pass
+  const double beta_new = kry->h_beta[k - 1] * nu;
+  kry->h_beta[k - 1] = beta_new;
+  LLZ_CUDA(cudaMemcpyAsync(kry->d_beta + (k - 1), kry->h_beta + (k - 1), sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  kry->k = k;  // iterations enqueued beyond k used the un-refined vector: drop them
+  kry->h_flag[0] = k;
+  if (shrink) *shrink = nu;
   return LLZ_OK;
 }
 

@@ -31,6 +31,8 @@ struct ScalarSink {
   const double* alpha_in = nullptr;  // device bank slot of alpha_{k-1} (copied to the host mirror)
   double* h_alpha = nullptr;      // mapped pinned host slots (may be null)
   double* h_beta = nullptr;
+  const double* wnorm2_in = nullptr;  // device: ||w'||^2 before the Gram-Schmidt pass (null => report beta itself)
+  double* h_wnorm = nullptr;      // mapped pinned slot receiving ||w'||
   long long* h_flag = nullptr;    // mapped pinned: set to `flag_value` after the scalars are visible
   long long flag_value = 0;
 };
@@ -39,12 +41,13 @@ int max_project_cols(int dtype);  // columns one projection launch can accumulat
 int max_update_cols(int dtype);
 int max_combine_cols(int dtype, int nvec);
 
-// h partials: ph[cta][ncols*NC] for the column chunk [col0, col0+ncols); returns the grid used.
+// h partials: ph[cta][ncols*NC + 1] for the column chunk [col0, col0+ncols); returns the grid used.
 int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n,
                    const Fold& fold, double* ph, int* grid_out);
 // coef[(col0+j)*NC+c] = sum_cta ph[cta][j*NC+c]  (+alpha at column j_alpha, +beta_prev at j_beta; -1 = none)
+// ph rows hold ncols*NC + 1 doubles: the last one is the CTA's partial of ||w'||^2, summed into *wnorm2 if non-null.
 int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, int j_alpha,
-                  const double* alpha, int j_beta, const double* beta_prev);
+                  const double* alpha, int j_beta, const double* beta_prev, double* wnorm2);
 // out = w - sum_j coef_j col_j over the chunk; if norm_partials != null, per-CTA partials of ||out||^2.
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
                   int64_t n, const double* coef, double* norm_partials, int* grid_out);

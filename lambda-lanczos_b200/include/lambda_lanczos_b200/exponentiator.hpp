@@ -70,8 +70,15 @@ class Exponentiator {
         check(llz_krylov_step(kry, mv_mul.get(), 0.0, orth), "llz_krylov_step");
         ++enqueued;
       }
-      double ak = 0, bk = 0;
-      check(llz_krylov_fetch(kry, (int64_t)k, &ak, &bk), "llz_krylov_fetch");
+      double ak = 0, bk = 0, wn = 0;
+      check(llz_krylov_fetch(kry, (int64_t)k, &ak, &bk, &wn), "llz_krylov_fetch");
+      for (int pass = 0; pass < 3 && full_orthogonalize && bk >= beta_threshold && bk < 0.5 * wn; ++pass) {  // DGKS, see LambdaLanczos
+        double shrink = 1.0;
+        check(llz_krylov_refine(kry, (int64_t)k, &shrink), "llz_krylov_refine");
+        enqueued = k;
+        wn = bk;
+        bk *= shrink;
+      }
       alpha.push_back(ak);  // :110
 
       // :124-133 — T_k = P diag(ev) P^T with the k-1 couplings known so far; coeff = exp(a T_k) e_0

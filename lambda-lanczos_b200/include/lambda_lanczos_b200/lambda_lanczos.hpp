@@ -120,6 +120,7 @@ struct RunStatistics {
   size_t iterations = 0;
   size_t runs = 0;
   uint64_t kernel_launches = 0;
+  size_t refinements = 0;  // Gram-Schmidt passes repeated because of cancellation
 };
 
 template <typename T>
@@ -146,6 +147,7 @@ class LambdaLanczos {
   int orthogonalization = LLZ_ORTH_FULL;  // llz_orth_t
   int pipeline_depth = 1;                 // iterations the GPU may run ahead of the host convergence test
   int ritz_solver = 0;                    // 0: bisection on the extreme values, 1: full implicit QL every iteration
+  double reorth_eta = 0.5;                // repeat the Gram-Schmidt pass when beta < reorth_eta * ||w'|| (DGKS)
 
   LambdaLanczos(DeviceOperator<T> mv_mul, size_t matrix_size, bool find_maximum, size_t num_eigs)
       : mv_mul(std::move(mv_mul)), matrix_size(matrix_size), max_iteration(matrix_size), find_maximum(find_maximum), num_eigs(num_eigs) {}
@@ -190,8 +192,19 @@ class LambdaLanczos {
         check(llz_krylov_step(kry, mv_mul.get(), (double)eigenvalue_offset, orthogonalization), "llz_krylov_step");
         ++enqueued;
       }
-      double a = 0, b = 0;
-      check(llz_krylov_fetch(kry, (int64_t)k, &a, &b), "llz_krylov_fetch");
+      double a = 0, b = 0, wn = 0;
+      check(llz_krylov_fetch(kry, (int64_t)k, &a, &b, &wn), "llz_krylov_fetch");
+      // DGKS test: if the Gram-Schmidt pass removed most of the vector (near breakdown, e.g. the Krylov space of a
+      // deflated run is exhausted), one classical pass leaves it non-orthogonal: repeat the pass ("twice is enough").
+      // The reference's modified Gram-Schmidt does not need this; it keeps the same vector to rounding.
+      for (int pass = 0; pass < 3 && orthogonalization != LLZ_ORTH_RECURRENCE && b >= zero_threshold && b < reorth_eta * wn; ++pass) {
+        double shrink = 1.0;
+        check(llz_krylov_refine(kry, (int64_t)k, &shrink), "llz_krylov_refine");
+        enqueued = k;
+        wn = b;
+        b *= shrink;
+        ++stats_.refinements;
+      }
       const auto t0 = clock::now();
       alpha.push_back(a);  // :248
       beta.push_back(b);   // :262
