@@ -301,14 +301,14 @@ int llz_vec_schmidt_orth(llz_vec_t w, const llz_vec_t* basis, int64_t count, int
       const int nc_cols = (int)((count - c0) < chunk ? (count - c0) : chunk);
       int grid = 0;
       LLZ_TRY(launch_project(ctx, w->dtype, cs, c0, nc_cols, w->d, w->n, nofold, ctx->d_ph, &grid));
-      LLZ_TRY(launch_reduce(ctx, w->dtype, ctx->d_ph, grid, c0, nc_cols, ctx->d_coef, -1, nullptr, -1, nullptr, nullptr));
+      LLZ_TRY(launch_reduce(ctx, w->dtype, ctx->d_ph, grid, c0, nc_cols, ctx->d_coef, nullptr));
     }
     LLZ_TRY(comm_allreduce_sum(ctx, ctx->d_coef, (int)count * nc));
     const int uchunk = max_update_cols(w->dtype);
     for (int c0 = 0; c0 < count; c0 += uchunk) {
       const int nc_cols = (int)((count - c0) < uchunk ? (count - c0) : uchunk);
       int grid = 0;
-      LLZ_TRY(launch_update(ctx, w->dtype, cs, c0, nc_cols, w->d, w->d, w->n, ctx->d_coef, nullptr, &grid));
+      LLZ_TRY(launch_update(ctx, w->dtype, cs, c0, nc_cols, w->d, w->d, w->n, ctx->d_coef, nofold, nullptr, &grid));
     }
   }
   return LLZ_OK;

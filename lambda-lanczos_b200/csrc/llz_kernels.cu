@@ -179,10 +179,6 @@ struct ReduceArgs {
   double* wnorm2;  // receives sum of the extra ||w'||^2 slot (may be null)
   int width;  // ncols*NC of the chunk; each CTA row of ph holds width + 1 doubles
   double* coef;  // already offset to the chunk
-  int i_alpha;   // index (in doubles, within the chunk) receiving +alpha, or -1
-  const double* alpha;
-  int i_beta;
-  const double* beta_prev;
 };
 
 __global__ void __launch_bounds__(128) k_reduce(ReduceArgs a) {
@@ -194,8 +190,6 @@ __global__ void __launch_bounds__(128) k_reduce(ReduceArgs a) {
     if (a.wnorm2) *a.wnorm2 = s;
     return;
   }
-  if (i == a.i_alpha) s += *a.alpha;
-  if (i == a.i_beta) s += *a.beta_prev;
   a.coef[i] = s;
 }
 
@@ -211,10 +205,21 @@ struct UpdateArgs {
   int64_t n;
   const double* coef;  // full coefficient array (indexed by absolute column)
   double* pb;          // norm partials or null
+  // Three-term recurrence, applied FIRST and with the very operation sequence k_project used, so that the w' this
+  // kernel starts from is bit-identical to the w' the coefficients were computed from.  (Folding alpha/beta into the
+  // coefficients instead would re-derive w' with different rounding, ~eps*||w|| in arbitrary directions, which is
+  // fatal near breakdown where ||w'|| << ||w||.)
+  int fold;                 // 0: none, 1: alpha*u1, 2: alpha*u1 + beta*u2
+  const double* alpha;      // device scalars
+  const double* beta_prev;
+  const void* u1;           // basis columns k-1 and k-2; their projection coefficients sit at coef[cu1], coef[cu2]
+  const void* u2;
+  int cu1, cu2;
 };
 
 template <class T, int VPT, bool FULL>
-__device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base, const T* cs) {
+__device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base, const T* cs, typename Num<T>::R alpha,
+                                              typename Num<T>::R beta, T h1, T h2) {
   constexpr int VEC = Num<T>::VEC;
   const int tid = threadIdx.x;
   const T* w = reinterpret_cast<const T*>(a.w);
@@ -224,6 +229,33 @@ __device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base,
   for (int i = 0; i < VPT; ++i) {
     const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
     acc[i] = FULL ? ld_plain(w + idx) : ld_guard(w, idx, a.n);
+  }
+  if (a.fold >= 1) {
+    const T* u1 = reinterpret_cast<const T*>(a.u1);
+    Pack<T> v1[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+      v1[i] = FULL ? ld_stream(u1 + idx) : ld_guard(u1, idx, a.n);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fnma_real(acc[i].e[e], alpha, v1[i].e[e]);
+    }
+    if (a.fold >= 2) {
+      const T* u2 = reinterpret_cast<const T*>(a.u2);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int64_t idx = base + (int64_t)(i * kThreads + tid) * VEC;
+        Pack<T> v2 = FULL ? ld_stream(u2 + idx) : ld_guard(u2, idx, a.n);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fnma_real(acc[i].e[e], beta, v2.e[e]);  // acc == w' of k_project, bit for bit
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fnma(acc[i].e[e], h2, v2.e[e]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) fnma(acc[i].e[e], h1, v1[i].e[e]);
   }
   int j0 = 0;
   for (; j0 + CT <= a.ncols; j0 += CT) {
@@ -283,12 +315,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
     cs[i] = from_double<T>(c[0], NC == 2 ? c[NC - 1] : 0.0);
   }
   __syncthreads();
+  using R = typename Num<T>::R;
+  R alpha = 0, beta = 0;
+  T h1 = zero_of(T()), h2 = zero_of(T());
+  if (a.fold >= 1) {
+    alpha = (R)(*a.alpha);
+    const double* c1 = a.coef + (size_t)a.cu1 * NC;
+    h1 = from_double<T>(c1[0], NC == 2 ? c1[NC - 1] : 0.0);
+    if (a.fold >= 2) {
+      beta = (R)(*a.beta_prev);
+      const double* c2 = a.coef + (size_t)a.cu2 * NC;
+      h2 = from_double<T>(c2[0], NC == 2 ? c2[NC - 1] : 0.0);
+    }
+  }
   constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
   const int64_t nslabs = (a.n + SLAB - 1) / SLAB;
   double nrm = 0.0;
   for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
     const int64_t base = s * SLAB;
-    nrm += (base + SLAB <= a.n) ? update_slab<T, VPT, true>(a, base, cs) : update_slab<T, VPT, false>(a, base, cs);
+    nrm += (base + SLAB <= a.n) ? update_slab<T, VPT, true>(a, base, cs, alpha, beta, h1, h2)
+                                : update_slab<T, VPT, false>(a, base, cs, alpha, beta, h1, h2);
   }
   if (a.pb) {
     const double t = block_sum(nrm, scratch);
@@ -682,8 +728,7 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
   return LLZ_OK;
 }
 
-int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, int j_alpha,
-                  const double* alpha, int j_beta, const double* beta_prev, double* wnorm2) {
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2) {
   const int nc = dtype_nc(dtype);
   ReduceArgs a;
   a.ph = ph;
@@ -691,10 +736,6 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
   a.wnorm2 = wnorm2;
   a.width = ncols * nc;
   a.coef = coef + (size_t)col0 * nc;
-  a.i_alpha = (j_alpha >= col0 && j_alpha < col0 + ncols) ? (j_alpha - col0) * nc : -1;
-  a.alpha = alpha;
-  a.i_beta = (j_beta >= col0 && j_beta < col0 + ncols) ? (j_beta - col0) * nc : -1;
-  a.beta_prev = beta_prev;
   k_reduce<<<(a.width + 1 + 127) / 128, 128, 0, ctx->stream>>>(a);
   return check_launch(ctx, "k_reduce");
 }
@@ -711,7 +752,7 @@ static int update_impl(llz_ctx_t ctx, const UpdateArgs& a, int* grid_out) {
 }
 
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
-                  int64_t n, const double* coef, double* norm_partials, int* grid_out) {
+                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out) {
   if (ncols < 0 || ncols > max_update_cols(dtype)) return fail(LLZ_ERR_INVALID, "update: %d columns per launch", ncols);
   UpdateArgs a;
   a.V = cs.V;
@@ -725,6 +766,16 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
   a.n = n;
   a.coef = coef;
   a.pb = norm_partials;
+  a.fold = fold.mode;
+  a.alpha = fold.alpha_out;
+  a.beta_prev = fold.beta_prev;
+  const size_t es = dtype_size(dtype);
+  a.u1 = cs.nv >= 1 ? (const char*)cs.V + (size_t)(cs.nv - 1) * cs.ld * es : nullptr;
+  a.u2 = cs.nv >= 2 ? (const char*)cs.V + (size_t)(cs.nv - 2) * cs.ld * es : nullptr;
+  a.cu1 = cs.nq + cs.nv - 1;
+  a.cu2 = cs.nq + cs.nv - 2;
+  if (a.fold >= 1 && (!a.u1 || !a.alpha)) return fail(LLZ_ERR_INVALID, "update: fold needs a previous basis column and alpha");
+  if (a.fold >= 2 && (!a.u2 || !a.beta_prev)) return fail(LLZ_ERR_INVALID, "update: fold=2 needs two previous basis columns and beta");
   LLZ_DISPATCH(dtype, {
     if (pick_vpt<T>(ctx, n) == 2) return update_impl<T, 2>(ctx, a, grid_out);
     return update_impl<T, 1>(ctx, a, grid_out);

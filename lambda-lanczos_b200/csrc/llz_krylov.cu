@@ -156,8 +156,7 @@ int ensure_ph(llz_krylov_t kry, size_t doubles) {
 
 // One classical Gram-Schmidt pass of `w` against cs: project -> reduce -> update (in place).  With an empty column
 // set only the update kernel runs (it then just produces the norm partials of w).
-int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, int j_alpha, int j_beta,
-             bool want_norm, int* norm_grid) {
+int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, bool want_norm, int* norm_grid) {
   llz_ctx_t ctx = kry->ctx;
   const int nc = dtype_nc(kry->dtype);
   const int total = cs.ncols();
@@ -173,27 +172,27 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, i
         LLZ_TRY(launch_project(ctx, kry->dtype, cs, c0, cols, w, kry->n, fold, kry->d_ph, &grid));
       }
       {
-        // the recurrence coefficients are added once per group: on rank 0, before the group-wide sum
-        const bool add = ctx->rank == 0;
         ProfScope ps(ctx, "reduce", 0.0);
-        LLZ_TRY(launch_reduce(ctx, kry->dtype, kry->d_ph, grid, c0, cols, kry->d_coef, add ? j_alpha : -1,
-                              fold.alpha_out, add ? j_beta : -1, fold.beta_prev,
+        LLZ_TRY(launch_reduce(ctx, kry->dtype, kry->d_ph, grid, c0, cols, kry->d_coef,
                               (c0 + cols >= total) ? kry->d_misc + 1 : nullptr));
       }
     }
     LLZ_TRY(comm_allreduce_sum(ctx, kry->d_coef, total * nc));
     LLZ_TRY(comm_allreduce_sum(ctx, kry->d_misc + 1, 1));
   }
+  // update: the fold.mode trailing basis columns are consumed by the kernel's recurrence prologue (first chunk)
+  const int generic = total - fold.mode;
   const int uchunk = max_update_cols(kry->dtype);
   int c0 = 0;
   do {
-    const int cols = std::min(uchunk, total - c0);
-    const bool last = c0 + cols >= total;
-    ProfScope ps(ctx, "update", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + 2));
-    LLZ_TRY(launch_update(ctx, kry->dtype, cs, c0, cols, w, w, kry->n, kry->d_coef,
+    const int cols = std::min(uchunk, generic - c0);
+    const bool last = c0 + cols >= generic;
+    Fold f = (c0 == 0) ? fold : Fold();
+    ProfScope ps(ctx, "update", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + f.mode + 2));
+    LLZ_TRY(launch_update(ctx, kry->dtype, cs, c0, cols, w, w, kry->n, kry->d_coef, f,
                           (last && want_norm) ? kry->d_pb : nullptr, norm_grid));
     c0 += cols;
-  } while (c0 < total);
+  } while (c0 < generic);
   return LLZ_OK;
 }
 
@@ -377,8 +376,8 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   Fold nofold;
   int grid = 0;
   // the start vector may lie almost inside span(locked): orthogonalise twice ("twice is enough")
-  if (kry->nq > 0) LLZ_TRY(cgs_pass(kry, cs, u0, nofold, -1, -1, false, &grid));
-  LLZ_TRY(cgs_pass(kry, cs, u0, nofold, -1, -1, true, &grid));
+  if (kry->nq > 0) LLZ_TRY(cgs_pass(kry, cs, u0, nofold, false, &grid));
+  LLZ_TRY(cgs_pass(kry, cs, u0, nofold, true, &grid));
   LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
   ScalarSink sink;
   sink.beta_out = kry->d_misc;
@@ -433,12 +432,10 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     cs.nv = (int)k;
     cs.Q = (const void* const*)kry->d_qptrs;
     cs.nq = kry->nq;
-    const int j_alpha = kry->nq + (int)k - 1;
-    const int j_beta = (k >= 2) ? kry->nq + (int)k - 2 : -1;
-    LLZ_TRY(cgs_pass(kry, cs, y, fold, j_alpha, j_beta, true, &grid));
+    LLZ_TRY(cgs_pass(kry, cs, y, fold, true, &grid));
     if (orth == LLZ_ORTH_FULL_TWICE) {
       Fold nofold;
-      LLZ_TRY(cgs_pass(kry, cs, y, nofold, -1, -1, true, &grid));
+      LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
     }
   }
   LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
@@ -495,7 +492,7 @@ int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink) {
   cs.nq = kry->nq;
   Fold nofold;
   int grid = 0;
-  LLZ_TRY(cgs_pass(kry, cs, y, nofold, -1, -1, true, &grid));
+  LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
   LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
   ScalarSink sink;
   sink.beta_out = kry->d_misc;

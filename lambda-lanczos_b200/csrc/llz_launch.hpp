@@ -44,13 +44,14 @@ int max_combine_cols(int dtype, int nvec);
 // h partials: ph[cta][ncols*NC + 1] for the column chunk [col0, col0+ncols); returns the grid used.
 int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n,
                    const Fold& fold, double* ph, int* grid_out);
-// coef[(col0+j)*NC+c] = sum_cta ph[cta][j*NC+c]  (+alpha at column j_alpha, +beta_prev at j_beta; -1 = none)
+// coef[(col0+j)*NC+c] = sum_cta ph[cta][j*NC+c]
 // ph rows hold ncols*NC + 1 doubles: the last one is the CTA's partial of ||w'||^2, summed into *wnorm2 if non-null.
-int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, int j_alpha,
-                  const double* alpha, int j_beta, const double* beta_prev, double* wnorm2);
-// out = w - sum_j coef_j col_j over the chunk; if norm_partials != null, per-CTA partials of ||out||^2.
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2);
+// out = w' - sum_j coef_j col_j over the chunk [col0, col0+ncols), where w' = w - alpha u_{k-1} - beta u_{k-2} per `fold`
+// (then the chunk must EXCLUDE those fold.mode trailing basis columns: the kernel applies their coefficients itself).
+// If norm_partials != null, per-CTA partials of ||out||^2.
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
-                  int64_t n, const double* coef, double* norm_partials, int* grid_out);
+                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out);
 // x *= 1/sqrt(sum partials); publishes beta (and alpha) per `sink`.  Leaves x untouched when the norm is not > 0.
 int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
                          const ScalarSink& sink);

@@ -251,6 +251,88 @@ void MULTIPLE_DEGENERATE_EIGENPAIRS() {  // :490-536 — 26 smallest of the peri
   std::printf("  Lanczos runs: %zu\n", engine.getIterationCounts().size());
 }
 
+// Diagnostic sweep of the degenerate ring: operator kind x start-vector policy (prints, never fails the suite)
+void DEGENERATE_SWEEP() {
+  const size_t n = 50;
+  const int num_eigs = 26;
+  vector<double> correct(num_eigs);
+  std::iota(correct.begin(), correct.end(), -num_eigs / 2);
+  for (auto& x : correct) x = -2.0 * std::cos(2.0 * M_PI * x / n);
+  std::sort(correct.begin(), correct.end());
+  vector<size_t> rows, cols;
+  vector<double> vals;
+  for (size_t i = 0; i < n; ++i) {
+    rows.push_back(i); cols.push_back((i + 1) % n); vals.push_back(-1.0);
+    rows.push_back((i + 1) % n); cols.push_back(i); vals.push_back(-1.0);
+  }
+  for (int opkind = 0; opkind < 2; ++opkind)
+    for (int seeded = 0; seeded < 2; ++seeded)
+      for (int depth = 0; depth < 2; ++depth) {
+        auto op = opkind == 0 ? chain_operator<double, double>(*g_ctx, n, -1.0, true) : DeviceOperator<double>::coo(*g_ctx, n, rows, cols, vals);
+        LambdaLanczos<double> engine(op, n, false, 1);
+        engine.num_eigs = num_eigs;
+        engine.eps = 1e-14;
+        engine.pipeline_depth = depth;
+        if (seeded) engine.init_vector = vector_initializer<double>;
+        vector<double> eigvals;
+        vector<vector<double>> eigvecs;
+        engine.run(eigvals, eigvecs);
+        double err = 0;
+        for (size_t i = 0; i < correct.size() && i < eigvals.size(); ++i) err = std::max(err, std::abs(correct[i] - eigvals[i]));
+        std::printf("  sweep op=%s start=%s depth=%d: max err %.3g, runs", opkind == 0 ? "callback" : "coo", seeded ? "seeded" : "random", depth, err);
+        for (auto c : engine.getIterationCounts()) std::printf(" %zu", c);
+        std::printf(", refinements %zu\n", engine.statistics().refinements);
+      }
+}
+
+// Per-run diagnostics of the degenerate ring with a fresh random start per run
+void DEGENERATE_TRACE() {
+  const size_t n = 50;
+  vector<size_t> rows, cols;
+  vector<double> vals;
+  for (size_t i = 0; i < n; ++i) {
+    rows.push_back(i); cols.push_back((i + 1) % n); vals.push_back(-1.0);
+    rows.push_back((i + 1) % n); cols.push_back(i); vals.push_back(-1.0);
+  }
+  auto op = DeviceOperator<double>::coo(*g_ctx, n, rows, cols, vals);
+  LambdaLanczos<double> engine(op, n, false, 26);
+  engine.eps = 1e-14;
+  engine.pipeline_depth = 0;
+  std::mt19937 gen(12345);
+  engine.init_vector = [&gen](vector<double>& v) {
+    std::uniform_real_distribution<double> d(-1, 1);
+    for (auto& x : v) x = d(gen);
+  };
+  vector<ll::DeviceVector<double>> locked;
+  vector<vector<double>> locked_host;
+  for (int run = 0; run < 4; ++run) {
+    vector<double> ev;
+    vector<ll::DeviceVector<double>> vec;
+    const size_t it = engine.run_iteration(ev, vec, 5, locked);
+    std::printf("  run %d: itern %zu, last beta %.3g\n", run, it, engine.last_beta().back());
+    for (size_t r = 0; r < ev.size(); ++r) {
+      vector<double> x = vec[r].to_host();
+      double res = 0, nrm = 0, maxov = 0;
+      for (size_t i = 0; i < n; ++i) {
+        const double ax = -x[(i + 1) % n] - x[(i + n - 1) % n];
+        res += (ax - ev[r] * x[i]) * (ax - ev[r] * x[i]);
+        nrm += x[i] * x[i];
+      }
+      for (auto& q : locked_host) {
+        double d = 0;
+        for (size_t i = 0; i < n; ++i) d += q[i] * x[i];
+        maxov = std::max(maxov, std::abs(d));
+      }
+      std::printf("    root %zu: lambda %.16g  k=%g  residual %.3g  norm-1 %.3g  max overlap with locked %.3g\n", r, ev[r],
+                  std::acos(-ev[r] / 2) * n / (2 * M_PI), std::sqrt(res), std::sqrt(nrm) - 1, maxov);
+    }
+    for (size_t r = 0; r < ev.size(); ++r) {
+      locked.push_back(vec[r]);
+      locked_host.push_back(vec[r].to_host());
+    }
+  }
+}
+
 template <typename T> double overlap_with(const vector<T>& a, const vector<T>& b) {
   T ip = T();
   double na = 0, nb = 0;
@@ -326,6 +408,8 @@ int main() {
     RUN(SINGLE_ELEMENT_MATRIX);
     RUN(MULTIPLE_EIGENPAIRS);
     RUN(MULTIPLE_DEGENERATE_EIGENPAIRS);
+    RUN(DEGENERATE_SWEEP);
+    RUN(DEGENERATE_TRACE);
     RUN(EXPONENTIATE_REAL);
     RUN(EXPONENTIATE_LARGE_MATRIX_AND_ZERO_DELTA);
   } catch (const std::exception& e) {
