@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this workload
+# at iteration k = 151 (profiles/r01_ncu_full_summary.txt); algorithmic bytes of those launches: 20.67 / 20.53 GB.
+NCU_TRAFFIC = {"project": 20.675e9, "update": 20.363e9}
+
 METRIC = "lanczos_iterations_per_second"
 UNIT = "iterations/s"
 
@@ -44,6 +48,8 @@ def parse_args():
     ap.add_argument("--num-eigs", type=int, default=4)
     ap.add_argument("--cpu-sample-iterations", type=int, default=0, help="max_iteration of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--format", default="sell", choices=["sell", "csr"],
+                    help="device storage of the operator: the user's CSR arrays as they are, or re-stored as SELL-32-sigma")
     return ap.parse_args()
 
 
@@ -199,6 +205,7 @@ def run_ours(args, rank, world):
     pkg = entry.load_package()
     wl = importlib.import_module("lambda_lanczos_b200.workloads")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
@@ -206,17 +213,38 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)
     n = args.nx * args.nx
-    csr = wl.laplacian2d_csr(args.nx)
-    start = wl.start_vector(n)
     if world > 1:
-        raise SystemExit("row-sharded multi-GPU runs are wired in a later commit")
+        # row-sharded group: rank 0 makes the communicator id, torch.distributed carries the 128-byte blob
+        blob = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            blob.copy_(torch.frombuffer(bytearray(pkg.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(blob, src=0)
+        ctx.join(rank, world, bytes(blob.cpu().numpy().tobytes()))
+    row0, n_local = wl.partition(n, rank, world)
+    csr = wl.laplacian2d_csr_rows(args.nx, row0, n_local) if world > 1 else wl.laplacian2d_csr(args.nx)
+    start_full = wl.start_vector(n)
+    start = np.ascontiguousarray(start_full[row0:row0 + n_local])
+
+    def make_op():
+        make = pkg.Operator.sell if args.format == "sell" else pkg.Operator.csr
+        return make(ctx, *csr, row0=row0, n_cols=n)
 
     def barrier():
         ctx.synchronize()
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident arm: operator already in HBM, eigenvectors stay on the device ----
-    op = pkg.Operator.csr(ctx, *csr)
+    op = make_op()
     eng = pkg.LambdaLanczos(op, n, False, args.num_eigs)
     eng.init_vector = start
     eng.max_iteration = args.max_iteration
@@ -243,25 +271,30 @@ def run_ours(args, rank, world):
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
-    dt = ev0.elapsed_time(ev1) * 1e-3  # device time of the K steps on the launching stream (host control included)
+    # device time of the K steps on the launching stream (host control included), max over the ranks
+    dt = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     launches = ctx.launch_count() - launches0
-    prof = {name: ctx.profile_read(name) for name in ("spmv", "project", "reduce", "update", "scale", "combine", "dot")}
+    prof = {name: ctx.profile_read(name) for name in ("spmv", "halo", "project", "reduce", "update", "scale", "combine", "dot")}
     ctx.profile(False)
     clocks = sampler.stop()
     value = iters / dt
 
-    # ---- roofline of the dominant kernel family (the two basis-streaming GEMV passes) ----
+    # ---- roofline of the dominant kernel family (the two basis-streaming GEMV passes), this rank's launches ----
     peak, peak_src = load_measured_peak()
     dom = max(("project", "update"), key=lambda k: prof[k][0])
     ms, cnt, by = prof[dom]
     achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     s = 8
-    model_bytes = bytes_model(n, s, op.bytes(), counts, args.num_eigs) * args.steps
+    a_bytes = op.bytes()
+    model_bytes = bytes_model(n_local, s, a_bytes, counts, args.num_eigs) * args.steps  # per GPU
     roofline = {"bound": "hbm", "kernel": f"k_{dom}<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": NCU_TRAFFIC.get(dom),
                 "launches": cnt, "avg_launch_ms": ms / max(cnt, 1), "algorithmic_bytes_per_launch": by / max(cnt, 1),
                 "kernel_time_share": {k: v[0] / (dt * 1e3) for k, v in prof.items() if v[1] > 0},
-                "whole_step_model_GBps": model_bytes / dt / 1e9, "whole_step_frac_of_peak": model_bytes / dt / 1e9 / peak}
+                "per_kernel_GBps": {k: v[2] / (v[0] * 1e-3) / 1e9 for k, v in prof.items() if v[0] > 0 and v[2] > 0},
+                "whole_step_model_GBps_per_gpu": model_bytes / dt / 1e9,
+                "whole_step_frac_of_peak": model_bytes / dt / 1e9 / peak,
+                "whole_step_frac_of_nominal_8TBps": model_bytes / dt / 1e9 / 8000.0}
 
     # ---- end-to-end arm: host CSR arrays in, host eigenvectors out, every step ----
     del eng, op
@@ -270,18 +303,17 @@ def run_ours(args, rank, world):
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))
     for _ in range(e2e_steps):
-        op2 = pkg.Operator.csr(ctx, *csr)  # H2D of the operator
+        op2 = make_op()  # H2D of the operator (this rank's row block)
         eng2 = pkg.LambdaLanczos(op2, n, False, args.num_eigs)
         eng2.init_vector = start
         eng2.max_iteration = args.max_iteration
-        evals2, evecs2 = eng2.run()  # H2D start vectors, D2H eigenvectors
+        evals2, evecs2 = eng2.run()  # H2D start vector, D2H eigenvectors
         e2e_iters += sum(eng2.getIterationCounts())
-        runs = len(eng2.getIterationCounts())
         del eng2, op2
     barrier()
-    e2e_dt = time.perf_counter() - t0
-    h2d = csr[0].nbytes // 2 + csr[1].nbytes + csr[2].nbytes + runs * start.nbytes  # row pointers travel as int32
-    d2h = evecs2.nbytes + 16 * e2e_iters // e2e_steps
+    e2e_dt = max_over_ranks(time.perf_counter() - t0)
+    h2d = (csr[0].nbytes // 2 + csr[1].nbytes + csr[2].nbytes + start.nbytes) * world  # row pointers travel as int32
+    d2h = evecs2.nbytes * world + 16 * e2e_iters // e2e_steps
     e2e = {"value": e2e_iters / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "seconds_per_step": e2e_dt / e2e_steps}
 
@@ -289,14 +321,21 @@ def run_ours(args, rank, world):
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "iterations_per_step": sum(counts), "lanczos_runs_per_step": len(counts),
-                       "l2": "inputs (basis of up to %d x 134 MB) far exceed the 126 MB L2" % (args.max_iteration + 1),
+                       "parallelism": f"rows{world}" if world > 1 else "single GPU",
+                       "operator_storage": "CSR input re-stored on the device as SELL-32-sigma" if args.format == "sell" else "CSR",
+                       "operator_bytes_per_gpu": int(a_bytes),
+                       "l2": "inputs (basis of up to %d x %d MB per GPU) far exceed the 126 MB L2" % (args.max_iteration + 1, n_local * 8 // 1000000),
                        "time_to_eigenpair_s": dt / args.steps, "wall_seconds_per_step": wall / args.steps, "host_seconds_per_step": host_s / args.steps,
                        "eigenvalues": [float(x) for x in evals]},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, wl, csr, start)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        ctx.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

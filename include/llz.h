@@ -73,6 +73,10 @@ int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* ctx);
 int llz_ctx_destroy(llz_ctx_t ctx);
 int llz_ctx_synchronize(llz_ctx_t ctx);
 int llz_ctx_stream(llz_ctx_t ctx, void** cuda_stream);
+/* A context keeps the device memory of destroyed vectors and of the last destroyed Krylov workspace (the mapped basis
+ * slab) for reuse by the next run — mapping tens of GB of HBM costs as much as hundreds of Lanczos iterations.
+ * This call returns all of it to the driver. */
+int llz_ctx_release_cache(llz_ctx_t ctx);
 /* Number of kernels this context has launched so far (the bench's "gpu_launches" evidence). */
 int llz_ctx_launch_count(llz_ctx_t ctx, uint64_t* count);
 /* Per-kernel-family device time (CUDA events on the context's stream) accumulated since profiling was last switched
@@ -86,6 +90,15 @@ int llz_ctx_profile_read(llz_ctx_t ctx, const char* name, double* ms, int64_t* l
 int llz_comm_unique_id(void* id128);
 int llz_ctx_join(llz_ctx_t ctx, int rank, int nranks, const void* id128);
 int llz_ctx_rank(llz_ctx_t ctx, int* rank, int* nranks);
+/* The row partition every built-in operator and the bench use: rank r owns [n*r/G, n*(r+1)/G).  Pure host arithmetic. */
+int llz_partition(int64_t n_global, int rank, int nranks, int64_t* row0, int64_t* n_local);
+/* Host-side halo planning for the local row block of a CSR matrix with GLOBAL column indices (no GPU involved):
+ * boundaries[0..nranks] are the row-block boundaries of the group.  Outputs (each may be NULL): the column indices in
+ * the local extended numbering ([0,n_rows) own block, n_rows + h = h-th halo entry), the sorted global columns of the
+ * halo entries (capacity halo_capacity), their number, and how many of them each rank owns. */
+int llz_halo_plan(int64_t n_rows, int64_t row0, const int64_t* rowptr, const int32_t* colidx, int nranks,
+                  const int64_t* boundaries, int32_t* colidx_local, int64_t* halo_cols, int64_t halo_capacity,
+                  int64_t* n_halo, int64_t* per_owner);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Operators — the device-side replacement of the `mv_mul` std::function
@@ -98,6 +111,12 @@ int llz_ctx_rank(llz_ctx_t ctx, int* rank, int* nranks);
  * column indices are global. */
 int llz_op_create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
                       const int32_t* colidx, const void* vals, int host_arrays, llz_op_t* op);
+/* SELL-C-sigma with C = 32 (one warp per slice): takes the same CSR arrays as llz_op_create_csr and re-stores them on
+ * the device in sliced-ELL form — coalesced, barrier-free SpMV for short-row matrices (stencils, lattice
+ * Hamiltonians).  sigma: 1 keeps the row order, a multiple of 32 (<= 1024) sorts windows of sigma rows by length to cut
+ * padding, 0 picks.  y is bit-identical to the CSR operator's (same per-row summation order). */
+int llz_op_create_sell(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
+                       const int32_t* colidx, const void* vals, int host_arrays, int sigma, llz_op_t* op);
 /* Matrix-free spin-1/2 XXZ chain  H = sum_b Jxy/2 (S+S- + h.c.) + Jz SzSz  on L sites in the sector with n_up up
  * spins, basis states in increasing integer order (BASELINE.json configs 4 and 5). */
 int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, double jz, double jxy, int periodic, llz_op_t* op);
@@ -108,6 +127,9 @@ int llz_op_create_callback(llz_ctx_t ctx, int dtype, int64_t n_local, llz_apply_
                            int overwrites_y, llz_op_t* op);
 int llz_op_destroy(llz_op_t op);
 int llz_op_rows(llz_op_t op, int64_t* n_local);
+/* Local rows, rows of the whole operator and first global row of the local block (n_global = n_local, row0 = 0 for a
+ * single rank).  The reference's `matrix_size` (lambda_lanczos.hpp:136) is n_global. */
+int llz_op_shape(llz_op_t op, int64_t* n_local, int64_t* n_global, int64_t* row0);
 /* Algorithmic bytes one apply has to move for the operator itself (A_bytes of SURVEY.md §8d; 0 for matrix-free). */
 int llz_op_bytes(llz_op_t op, int64_t* bytes);
 /* y = A x on device vectors (stand-alone use and Exponentiator::taylor_run, exponentiator.hpp:191). */

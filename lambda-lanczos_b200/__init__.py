@@ -90,6 +90,20 @@ class Context:
         self.h = vp()
         _check(lib().llz_ctx_create(C.c_int(device), C.byref(self.h)), "llz_ctx_create")
         self.device = device
+        self.rank, self.nranks = 0, 1
+
+    @staticmethod
+    def unique_id() -> bytes:
+        """128-byte blob identifying a new row-sharded group; make it on rank 0 and hand it to every rank."""
+        buf = (C.c_ubyte * 128)()
+        _check(lib().llz_comm_unique_id(buf), "llz_comm_unique_id")
+        return bytes(buf)
+
+    def join(self, rank: int, nranks: int, comm_id: bytes):
+        """Join a row-sharded group (one process per GPU, NCCL underneath): vectors become local row blocks."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(comm_id)
+        _check(lib().llz_ctx_join(self.h, C.c_int(rank), C.c_int(nranks), buf), "llz_ctx_join")
+        self.rank, self.nranks = rank, nranks
 
     def synchronize(self):
         _check(lib().llz_ctx_synchronize(self.h), "llz_ctx_synchronize")
@@ -98,6 +112,10 @@ class Context:
         c = C.c_uint64(0)
         _check(lib().llz_ctx_launch_count(self.h, C.byref(c)), "llz_ctx_launch_count")
         return int(c.value)
+
+    def release_cache(self):
+        """Give the cached device memory (vector pool, mapped Krylov basis of the last run) back to the driver."""
+        _check(lib().llz_ctx_release_cache(self.h), "llz_ctx_release_cache")
 
     def profile(self, enable: bool):
         _check(lib().llz_ctx_profile(self.h, C.c_int(int(enable))), "llz_ctx_profile")
@@ -128,18 +146,38 @@ class Context:
 class Operator:
     """Device operator (``llz_op_t``): the replacement of the reference's ``mv_mul`` std::function."""
 
-    def __init__(self, ctx: Context, handle, dtype, n):
-        self.ctx, self.h, self.dtype, self.n = ctx, handle, np.dtype(dtype), int(n)
+    def __init__(self, ctx: Context, handle, dtype, n=None):
+        self.ctx, self.h, self.dtype = ctx, handle, np.dtype(dtype)
+        nl, ng, r0 = i64(0), i64(0), i64(0)
+        _check(lib().llz_op_shape(handle, C.byref(nl), C.byref(ng), C.byref(r0)), "llz_op_shape")
+        self.n, self.n_global, self.row0 = int(nl.value), int(ng.value), int(r0.value)  # n = rows of the LOCAL block
 
     @classmethod
-    def csr(cls, ctx: Context, rowptr, colidx, vals):
+    def csr(cls, ctx: Context, rowptr, colidx, vals, row0: int = 0, n_cols: int | None = None):
+        """CSR operator.  In a joined context pass the local row block: ``rowptr`` local (starts at 0), ``colidx``
+        GLOBAL, ``row0`` the first global row and ``n_cols`` the global dimension."""
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
         colidx = np.ascontiguousarray(colidx, dtype=np.int32)
         vals = np.ascontiguousarray(vals)
         n = rowptr.size - 1
         h = vp()
-        _check(lib().llz_op_create_csr(ctx.h, C.c_int(dtype_code(vals.dtype)), i64(n), i64(n), i64(0), _ptr(rowptr),
-                                       _ptr(colidx), _ptr(vals), C.c_int(1), C.byref(h)), "llz_op_create_csr")
+        _check(lib().llz_op_create_csr(ctx.h, C.c_int(dtype_code(vals.dtype)), i64(n), i64(n if n_cols is None else n_cols),
+                                       i64(row0), _ptr(rowptr), _ptr(colidx), _ptr(vals), C.c_int(1), C.byref(h)),
+               "llz_op_create_csr")
+        return cls(ctx, h, vals.dtype, n)
+
+    @classmethod
+    def sell(cls, ctx: Context, rowptr, colidx, vals, sigma: int = 0, row0: int = 0, n_cols: int | None = None):
+        """SELL-32-sigma operator built on the device from CSR arrays (same arguments as :meth:`csr`); ``sigma`` = 1
+        keeps the row order, a multiple of 32 sorts windows of that many rows by length, 0 picks."""
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        vals = np.ascontiguousarray(vals)
+        n = rowptr.size - 1
+        h = vp()
+        _check(lib().llz_op_create_sell(ctx.h, C.c_int(dtype_code(vals.dtype)), i64(n), i64(n if n_cols is None else n_cols),
+                                        i64(row0), _ptr(rowptr), _ptr(colidx), _ptr(vals), C.c_int(1), C.c_int(sigma), C.byref(h)),
+               "llz_op_create_sell")
         return cls(ctx, h, vals.dtype, n)
 
     @classmethod
@@ -310,7 +348,7 @@ class LambdaLanczos:
     (lambda_lanczos.hpp:126-181,200); ``run()`` returns (eigenvalues, eigenvectors) like lambda_lanczos.hpp:376."""
 
     def __init__(self, mv_mul: Operator, matrix_size: int, find_maximum: bool, num_eigs: int = 1):
-        assert mv_mul.n == matrix_size
+        assert mv_mul.n_global == matrix_size  # row-sharded: matrix_size is the global dimension
         self.mv_mul = mv_mul
         self.matrix_size = matrix_size
         self.max_iteration = matrix_size
@@ -319,7 +357,8 @@ class LambdaLanczos:
         self.num_eigs = num_eigs
         self.eigenvalue_offset = 0.0
         self.num_eigs_per_iteration = 5
-        self.init_vector = None  # host array handed out at the start of every Lanczos run; None = seeded default
+        # host array handed out at the start of every Lanczos run (row-sharded: the LOCAL block); None = seeded default
+        self.init_vector = None
         self.orthogonalization = ORTH_FULL
         self.pipeline_depth = 1
         self.ritz_solver = 0
@@ -329,11 +368,12 @@ class LambdaLanczos:
 
     def run(self):
         op = self.mv_mul
-        n = self.matrix_size
+        n = op.n  # eigenvectors come back as local row blocks
         p = EigsParams(int(self.find_maximum), self.num_eigs, float(self.eigenvalue_offset), float(self.eps),
                        int(self.max_iteration), int(self.num_eigs_per_iteration), int(self.orthogonalization),
                        int(self.pipeline_depth), int(self.ritz_solver))
         start = None if self.init_vector is None else np.ascontiguousarray(self.init_vector, dtype=op.dtype)
+        assert start is None or start.size == n, "init_vector must have the operator's (local) row count"
         evals = np.zeros(self.num_eigs, dtype=np.float64)
         evecs = np.zeros((self.num_eigs, n), dtype=op.dtype) if self.want_eigenvectors else None
         iters = np.zeros(256, dtype=np.int64)
@@ -355,7 +395,7 @@ class Exponentiator:
     """``Exponentiator(mv_mul, n).run(a, input)`` -> (iterations, output)  (exponentiator.hpp:80,87-173)."""
 
     def __init__(self, mv_mul: Operator, matrix_size: int):
-        assert mv_mul.n == matrix_size
+        assert mv_mul.n_global == matrix_size
         self.mv_mul = mv_mul
         self.matrix_size = matrix_size
         self.max_iteration = matrix_size
@@ -365,7 +405,8 @@ class Exponentiator:
     def _run(self, a, x, taylor):
         op = self.mv_mul
         x = np.ascontiguousarray(x, dtype=op.dtype)
-        out = np.empty(self.matrix_size, dtype=op.dtype)
+        assert x.size == op.n
+        out = np.empty(op.n, dtype=op.dtype)
         z = complex(a)
         it = i64(0)
         _check(lib().llz_expm_run(op.ctx.h, op.h, C.c_int(dtype_code(op.dtype)), (C.c_double * 2)(z.real, z.imag), _ptr(x),

@@ -7,6 +7,7 @@
 // the alpha / beta^2 scalars.
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "llz_launch.hpp"
@@ -63,6 +64,29 @@ int comm_exchange(llz_ctx_t ctx, const char* send_base, const size_t* send_off, 
   }
   LLZ_NCCL(ncclGroupEnd());
   return LLZ_OK;
+}
+
+// Host-to-host all-gather of a small fixed-size record per rank (set-up time only: goes through device scratch and
+// synchronises the stream).
+int comm_allgather_host(llz_ctx_t ctx, const void* send, void* recv, size_t bytes_per_rank) {
+  if (ctx->nranks == 1) {
+    memcpy(recv, send, bytes_per_rank);
+    return LLZ_OK;
+  }
+  void* d_send = nullptr;
+  void* d_recv = nullptr;
+  LLZ_CUDA(cudaMalloc(&d_send, std::max<size_t>(bytes_per_rank, 16)));
+  LLZ_CUDA(cudaMalloc(&d_recv, std::max<size_t>(bytes_per_rank * ctx->nranks, 16)));
+  LLZ_CUDA(cudaMemcpyAsync(d_send, send, bytes_per_rank, cudaMemcpyHostToDevice, ctx->stream));
+  int s = comm_allgather_bytes(ctx, d_send, d_recv, bytes_per_rank);
+  if (s == LLZ_OK) {
+    cudaError_t e = cudaMemcpyAsync(recv, d_recv, bytes_per_rank * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) s = fail(LLZ_ERR_CUDA, "allgather_host: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  return s;
 }
 
 void comm_destroy(llz_ctx_t ctx) {

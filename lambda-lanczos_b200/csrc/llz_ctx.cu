@@ -24,6 +24,61 @@ int fail(int status, const char* fmt, ...) {
   return status;
 }
 
+cudaError_t dev_malloc(llz_ctx_t ctx, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation && (ctx->cached_krylov || !ctx->vec_pool.empty())) {
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    ctx_trim(ctx);
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+
+int ctx_alloc(llz_ctx_t ctx, size_t bytes, void** out) {
+  auto it = ctx->vec_pool.find(bytes);
+  if (it != ctx->vec_pool.end()) {
+    *out = it->second;
+    ctx->vec_pool.erase(it);
+    ctx->vec_pool_bytes -= bytes;
+    return LLZ_OK;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cached buffers back and try once more
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    ctx_trim(ctx);
+    e = cudaMalloc(out, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  return LLZ_OK;
+}
+
+void ctx_free(llz_ctx_t ctx, void* p, size_t bytes) {
+  if (!p) return;
+  if (ctx->vec_pool_bytes + bytes <= ctx->vec_pool_limit) {
+    ctx->vec_pool.emplace(bytes, p);
+    ctx->vec_pool_bytes += bytes;
+    return;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(p);
+}
+
+void ctx_trim(llz_ctx_t ctx) {
+  for (auto& kv : ctx->vec_pool) cudaFree(kv.second);
+  ctx->vec_pool.clear();
+  ctx->vec_pool_bytes = 0;
+  if (ctx->cached_krylov) {
+    llz_krylov_t k = ctx->cached_krylov;
+    ctx->cached_krylov = nullptr;
+    krylov_destroy_now(k);
+  }
+}
+
 }  // namespace llz
 
 using namespace llz;
@@ -67,6 +122,7 @@ int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  ctx->vec_pool_limit = (size_t)prop.totalGlobalMem / 4;
   if (cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
@@ -96,6 +152,14 @@ int llz_ctx_synchronize(llz_ctx_t ctx) {
 int llz_ctx_stream(llz_ctx_t ctx, void** s) {
   if (!ctx || !s) return fail(LLZ_ERR_INVALID, "null argument");
   *s = (void*)ctx->stream;
+  return LLZ_OK;
+}
+
+int llz_ctx_release_cache(llz_ctx_t ctx) {
+  if (!ctx) return fail(LLZ_ERR_INVALID, "null ctx");
+  LLZ_CUDA(cudaSetDevice(ctx->device));
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx_trim(ctx);
   return LLZ_OK;
 }
 
@@ -159,11 +223,10 @@ int llz_vec_create(llz_ctx_t ctx, int dtype, int64_t n, llz_vec_t* out) {
   v->dtype = dtype;
   v->n = n;
   const size_t bytes = ((size_t)n * dtype_size(dtype) + 255) / 256 * 256 + 256;
-  cudaError_t e = cudaMalloc(&v->d, bytes);
-  if (e != cudaSuccess) {
+  const int st = ctx_alloc(ctx, bytes, &v->d);
+  if (st != LLZ_OK) {
     delete v;
-    return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "cudaMalloc(%zu): %s", bytes,
-                cudaGetErrorString(e));
+    return st;
   }
   *out = v;
   return LLZ_OK;
@@ -171,10 +234,7 @@ int llz_vec_create(llz_ctx_t ctx, int dtype, int64_t n, llz_vec_t* out) {
 
 int llz_vec_destroy(llz_vec_t v) {
   if (!v) return LLZ_OK;
-  if (v->owned && v->d) {
-    cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->d);
-  }
+  if (v->owned && v->d) ctx_free(v->ctx, v->d, ((size_t)v->n * dtype_size(v->dtype) + 255) / 256 * 256 + 256);
   delete v;
   return LLZ_OK;
 }
@@ -232,7 +292,7 @@ int llz_vec_dot(llz_vec_t a, llz_vec_t b, double out[2]) {
 
 int llz_vec_norm(llz_vec_t v, double* out) {
   if (!v || !out) return fail(LLZ_ERR_INVALID, "null");
-  double d[2];
+  double d[2] = {0.0, 0.0};
   LLZ_TRY(dot_to_host(v->ctx, v->dtype, v->d, v->d, v->n, d));
   *out = sqrt(d[0]);
   return LLZ_OK;
@@ -318,6 +378,7 @@ int llz_ctx_destroy(llz_ctx_t ctx) {
   if (!ctx) return LLZ_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ctx_trim(ctx);
   comm_destroy(ctx);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_result) cudaFree(ctx->d_result);

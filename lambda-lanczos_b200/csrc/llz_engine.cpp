@@ -19,8 +19,8 @@ int eigs_run(llz_ctx_t ctx, llz_op_t op, const llz_eigs_params_t* p, const void*
   using R = util::real_t<T>;
   Context c = Context::borrow(ctx);
   DeviceOperator<T> A = DeviceOperator<T>::borrow(c, op);
-  const size_t n = A.rows();
-  LambdaLanczos<T> engine(A, n, p->find_maximum != 0, (size_t)p->num_eigs);
+  const size_t n = A.rows();  // local block
+  LambdaLanczos<T> engine(A, A.global_rows(), p->find_maximum != 0, (size_t)p->num_eigs);
   engine.eigenvalue_offset = (R)p->eigenvalue_offset;
   if (p->eps > 0) engine.eps = (R)p->eps;
   if (p->max_iteration > 0) engine.max_iteration = (size_t)p->max_iteration;
@@ -29,8 +29,7 @@ int eigs_run(llz_ctx_t ctx, llz_op_t op, const llz_eigs_params_t* p, const void*
   engine.pipeline_depth = p->pipeline_depth;
   engine.ritz_solver = p->ritz_solver;
   if (start) {
-    const T* s = static_cast<const T*>(start);
-    engine.init_vector = [s, n](std::vector<T>& v) { std::memcpy(v.data(), s, sizeof(T) * n); };
+    engine.start_local = static_cast<const T*>(start);
   } else {
     engine.init_vector = [](std::vector<T>& v) {  // seeded, so that C-ABI callers get reproducible runs by default
       std::mt19937 gen(1);
@@ -68,8 +67,8 @@ int expm_run(llz_ctx_t ctx, llz_op_t op, const double a[2], const void* input, v
   using R = util::real_t<T>;
   Context c = Context::borrow(ctx);
   DeviceOperator<T> A = DeviceOperator<T>::borrow(c, op);
-  const size_t n = A.rows();
-  Exponentiator<T> ex(A, n);
+  const size_t n = A.rows();  // local block
+  Exponentiator<T> ex(A, A.global_rows());
   if (eps > 0) ex.eps = (R)eps;
   if (max_iteration > 0) ex.max_iteration = (size_t)max_iteration;
   ex.full_orthogonalize = full_orth != 0;

@@ -70,6 +70,13 @@ struct llz_ctx_s {
   double* d_ph = nullptr;        // h partials for llz_vec_schmidt_orth
   size_t ph_capacity = 0;
   int64_t ptr_capacity = 0;
+  // Device-memory cache of the context (SURVEY.md §8b "ownership": the basis slab and work vectors are owned by the
+  // ctx and reused across runs).  Everything runs on ONE stream, so a buffer handed back can be reused by later
+  // stream-ordered work without a synchronisation.
+  std::multimap<size_t, void*> vec_pool;  // free device buffers by size
+  size_t vec_pool_bytes = 0;
+  size_t vec_pool_limit = 0;              // set at creation (a quarter of the device memory)
+  llz_krylov_t cached_krylov = nullptr;   // last destroyed Krylov workspace, revived by a matching llz_krylov_create
   // profiling
   bool profile = false;
   std::map<std::string, llz::ProfEntry> prof;
@@ -93,8 +100,16 @@ struct OpBase {
   llz_ctx_t ctx = nullptr;
   int dtype = 0;
   int64_t n_local = 0;
+  int64_t n_global = 0;  // rows of the whole operator (= n_local for a single rank)
+  int64_t row0 = 0;      // first global row of the local block
   int64_t bytes = 0;
   virtual ~OpBase() {}
+  // Row-sharded operators: make the remote entries of x that the local rows reference available (halo exchange /
+  // all-gather over NCCL, enqueued on ctx->stream).  Called once before every apply_fused.
+  virtual int prepare(const void* x) {
+    (void)x;
+    return LLZ_OK;
+  }
   // y = A x + sigma x ; per-CTA partials of Re<x,y> into alpha_partials[0..*n_partials) (device), all on ctx->stream.
   // Returns LLZ_OK or an error.  Implementations that cannot fuse the dot leave *n_partials = 0 and the engine runs
   // a separate dot kernel.
@@ -110,6 +125,20 @@ int comm_allreduce_sum(llz_ctx_t ctx, double* d, int count);
 // (d[0], *count = 1).
 int comm_allreduce_partials(llz_ctx_t ctx, double* d, int* count);
 void comm_destroy(llz_ctx_t ctx);
+// Pooled device allocations of a context (llz_ctx.cu)
+int ctx_alloc(llz_ctx_t ctx, size_t bytes, void** out);
+void ctx_free(llz_ctx_t ctx, void* p, size_t bytes);
+// cudaMalloc that gives the context's cached memory back to the driver and retries once when the device is full
+cudaError_t dev_malloc(llz_ctx_t ctx, void** p, size_t bytes);
+template <class P> inline cudaError_t dev_malloc(llz_ctx_t ctx, P** p, size_t bytes) { return dev_malloc(ctx, (void**)p, bytes); }
+void ctx_trim(llz_ctx_t ctx);            // release every cached buffer (vector pool + cached Krylov workspace)
+void krylov_destroy_now(llz_krylov_t k); // really free a workspace (llz_krylov.cu)
+int comm_allgather_bytes(llz_ctx_t ctx, const void* send, void* recv, size_t bytes_per_rank);
+int comm_allgather_host(llz_ctx_t ctx, const void* send, void* recv, size_t bytes_per_rank);
+// Grouped point-to-point exchange (device buffers): for every peer p send send_bytes[p] from send_base + send_off[p]
+// and receive recv_bytes[p] into recv_base + recv_off[p].
+int comm_exchange(llz_ctx_t ctx, const char* send_base, const size_t* send_off, const size_t* send_bytes, char* recv_base,
+                  const size_t* recv_off, const size_t* recv_bytes);
 
 // RAII: records a start/stop event pair around the launches issued in its scope when ctx->profile is on.
 struct ProfScope {

@@ -61,6 +61,7 @@ struct llz_krylov_s {
   int64_t ld = 0;        // elements per column slot
   size_t col_bytes = 0;  // ld * sizeof(T)
   int64_t cap_cols = 0;  // columns the store may ever hold
+  int64_t requested_cols = 0;  // max_cols the creator asked for (cache key)
   // basis store
   bool use_vmm = false;
   CUdeviceptr va = 0;
@@ -204,9 +205,22 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
   if (!ctx || !out || n < 1 || max_cols < 2 || dtype_size(dtype) == 0)
     return fail(LLZ_ERR_INVALID, "krylov_create: bad argument (n=%lld, max_cols=%lld)", (long long)n, (long long)max_cols);
   LLZ_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->cached_krylov) {
+    llz_krylov_t c = ctx->cached_krylov;
+    ctx->cached_krylov = nullptr;
+    if (c->dtype == dtype && c->n == n && c->requested_cols == max_cols) {  // revive: mapped basis memory is kept
+      c->k = 0;
+      c->nq = 0;
+      c->h_flag[0] = 0;
+      *out = c;
+      return LLZ_OK;
+    }
+    krylov_destroy_now(c);
+  }
   const size_t es = dtype_size(dtype);
   llz_krylov_t kry = new llz_krylov_s();
   kry->ctx = ctx;
+  kry->requested_cols = max_cols;
   kry->dtype = dtype;
   kry->n = n;
   // column slots: 256-byte aligned, plus a 1280-byte skew so that consecutive columns of a power-of-two sized
@@ -278,7 +292,7 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
   kry->h_flag[0] = 0;
   int s = ensure_cols(kry, 2);
   if (s != LLZ_OK) {
-    llz_krylov_destroy(kry);
+    krylov_destroy_now(kry);
     return s;
   }
   *out = kry;
@@ -287,6 +301,18 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
 
 int llz_krylov_destroy(llz_krylov_t kry) {
   if (!kry) return LLZ_OK;
+  llz_ctx_t ctx = kry->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->cached_krylov) krylov_destroy_now(ctx->cached_krylov);
+  ctx->cached_krylov = kry;  // keep the mapped basis for the next run on this context (llz_ctx_release_cache frees it)
+  return LLZ_OK;
+}
+
+}  // extern "C"
+
+void llz::krylov_destroy_now(llz_krylov_t kry) {
+  if (!kry) return;
   cudaSetDevice(kry->ctx->device);
   cudaStreamSynchronize(kry->ctx->stream);
   if (kry->use_vmm) {
@@ -317,8 +343,9 @@ int llz_krylov_destroy(llz_krylov_t kry) {
   cudaFreeHost(kry->h_wnorm);
   cudaFreeHost(kry->h_flag);
   delete kry;
-  return LLZ_OK;
 }
+
+extern "C" {
 
 int llz_krylov_capacity(llz_krylov_t kry, int64_t* max_cols) {
   if (!kry || !max_cols) return fail(LLZ_ERR_INVALID, "null");
@@ -403,6 +430,7 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
   void* y = kry->col(k);
 
   int npa = 0;
+  LLZ_TRY(op->impl->prepare(x));
   {
     ProfScope ps(ctx, "spmv", (double)op->impl->bytes + (double)kry->n * (double)dtype_size(kry->dtype) * 2);
     LLZ_TRY(op->impl->apply_fused(x, y, sigma, kry->d_pa, &npa));

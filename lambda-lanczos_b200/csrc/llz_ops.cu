@@ -25,10 +25,22 @@ template <> __device__ __forceinline__ double2 shfl_down_t(double2 v, int o, int
   return make_double2(__shfl_down_sync(0xffffffffu, v.x, o, w), __shfl_down_sync(0xffffffffu, v.y, o, w));
 }
 
+// Column indices of a row-sharded operator use the local "extended" numbering (llz_halo.cpp): [0, nloc) addresses the
+// rank's own block of x, nloc + h the h-th entry of the halo buffer filled by the exchange before the launch.
+template <class T> __device__ __forceinline__ T gather_x(const T* __restrict__ x, const T* __restrict__ halo, int32_t c, int32_t nloc) {
+  return (c < nloc) ? __ldg(x + c) : __ldg(halo + (c - nloc));
+}
+
+// sendbuf[i] = x[idx[i]]: the entries of the local block the peers asked for, grouped by peer.
+template <class T> __global__ void __launch_bounds__(kThreads) k_pack(const T* __restrict__ x, const int32_t* __restrict__ idx, T* __restrict__ out, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads) out[i] = __ldg(x + idx[i]);
+}
+
 template <class T, class IDX, int LPR>
 __global__ void __launch_bounds__(kThreads, 4)
     k_csr_spmv_dot(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
-                   const T* __restrict__ x, T* __restrict__ y, int64_t n, typename Num<T>::R sigma, double* pa) {
+                   const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
+                   typename Num<T>::R sigma, double* pa) {
   __shared__ double scratch[kWarps];
   constexpr int ROWS = kThreads / LPR;
   const int tid = threadIdx.x;
@@ -39,7 +51,7 @@ __global__ void __launch_bounds__(kThreads, 4)
     T sum = zero_of(T());
     if (row < n) {
       const IDX p1 = rowptr[row + 1];
-      for (IDX p = rowptr[row] + sub; p < p1; p += LPR) fmadd(sum, vals[p], __ldg(x + colidx[p]));
+      for (IDX p = rowptr[row] + sub; p < p1; p += LPR) fmadd(sum, vals[p], gather_x(x, halo, colidx[p], nloc));
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) sum = add_t(sum, shfl_down_t(sum, o, LPR));
@@ -66,8 +78,8 @@ __global__ void __launch_bounds__(kThreads, 4)
 template <class T, class IDX>
 __global__ void __launch_bounds__(kThreads, 4)
     k_csr_stream_dot(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
-                     const T* __restrict__ x, T* __restrict__ y, int64_t n, typename Num<T>::R sigma, double* pa, int R,
-                     int cap) {
+                     const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
+                     typename Num<T>::R sigma, double* pa, int R, int cap) {
   extern __shared__ __align__(16) unsigned char smem_s[];
   T* prod = reinterpret_cast<T*>(smem_s);
   IDX* rp = reinterpret_cast<IDX*>(prod + cap);
@@ -82,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 4)
     __syncthreads();
     const IDX base = rp[0];
     const int cnt = (int)(rp[nrows] - base);
-    for (int e = tid; e < cnt; e += kThreads) prod[e] = mul(vals[base + e], __ldg(x + colidx[base + e]));
+    for (int e = tid; e < cnt; e += kThreads) prod[e] = mul(vals[base + e], gather_x(x, halo, colidx[base + e], nloc));
     __syncthreads();
     for (int r = tid; r < nrows; r += kThreads) {
       const int j1 = (int)(rp[r + 1] - base);
@@ -99,6 +111,123 @@ __global__ void __launch_bounds__(kThreads, 4)
   if (tid == 0) pa[blockIdx.x] = t;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SELL-C-sigma (C = 32 = one warp per slice): rows are grouped in slices of 32, each slice stored column-major and
+// padded to its longest row, so lane l of a warp walks row l of the slice with perfectly coalesced 128/256-byte
+// accesses and no shared-memory staging or block barriers.  Rows may be sorted by length inside windows of sigma rows
+// (perm) to cut the padding of irregular matrices.  Padding entries carry column -1 and are skipped (never 0 * x, so
+// Inf/NaN in x cannot leak into rows that do not reference them).  Within a row the products are added in column
+// order with separate multiply and add — the order and rounding of a sequential CSR loop (the reference's sample-style
+// mv_mul), so y is bit-identical to the CSR kernels' and to the CPU's.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSellC = 32;
+
+template <class IDX> __global__ void __launch_bounds__(kThreads) k_sell_rowlen(const IDX* __restrict__ rowptr, int64_t n, int32_t* __restrict__ len) {
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads)
+    len[r] = (int32_t)(rowptr[r + 1] - rowptr[r]);
+}
+
+// One CTA (sigma threads) per window: stable sort of the window's rows by decreasing length, by ranking.
+__global__ void k_sell_sort(const int32_t* __restrict__ len, int64_t n, int sigma, int32_t* __restrict__ perm) {
+  extern __shared__ int32_t lens[];
+  const int i = threadIdx.x;
+  const int64_t row = (int64_t)blockIdx.x * sigma + i;
+  const int32_t mine = row < n ? len[row] : -1;
+  lens[i] = mine;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < sigma; ++j) {
+    const int32_t o = lens[j];
+    rank += (o > mine) || (o == mine && j < i);
+  }
+  if (row < n) perm[(int64_t)blockIdx.x * sigma + rank] = (int32_t)row;
+}
+
+// width[s] = longest row of slice s (one warp per slice)
+__global__ void __launch_bounds__(kThreads) k_sell_width(const int32_t* __restrict__ len, const int32_t* __restrict__ perm, int64_t n,
+                                                         int64_t n_slices, int32_t* __restrict__ width) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t s = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s < n_slices; s += (int64_t)gridDim.x * kWarps) {
+    const int64_t r = s * kSellC + lane;
+    int32_t w = 0;
+    if (r < n) w = len[perm ? perm[r] : r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0) width[s] = w;
+  }
+}
+
+template <class T, class IDX>
+__global__ void __launch_bounds__(kThreads) k_sell_fill(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
+                                                        const int32_t* __restrict__ perm, const int64_t* __restrict__ slice_ptr, int64_t n,
+                                                        int64_t n_slices, int32_t* __restrict__ scol, T* __restrict__ sval) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t s = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s < n_slices; s += (int64_t)gridDim.x * kWarps) {
+    const int64_t p0 = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - p0) / kSellC);
+    const int64_t r = s * kSellC + lane;
+    IDX q0 = 0;
+    int len = 0;
+    if (r < n) {
+      const int64_t src = perm ? perm[r] : r;
+      q0 = rowptr[src];
+      len = (int)(rowptr[src + 1] - q0);
+    }
+    for (int j = 0; j < w; ++j) {
+      const int64_t dst = p0 + (int64_t)j * kSellC + lane;
+      scol[dst] = j < len ? colidx[q0 + j] : -1;
+      sval[dst] = j < len ? vals[q0 + j] : zero_of(T());
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads, 4)
+    k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
+                    const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
+                    T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa) {
+  __shared__ double scratch[kWarps];
+  const int lane = threadIdx.x & 31;
+  double dot = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s < n_slices; s += (int64_t)gridDim.x * kWarps) {
+    const int64_t p0 = __ldg(slice_ptr + s);
+    const int w = (int)((__ldg(slice_ptr + s + 1) - p0) / kSellC);
+    const int32_t* __restrict__ cp = scol + p0 + lane;
+    const T* __restrict__ vp = sval + p0 + lane;
+    T sum = zero_of(T());
+    int j = 0;
+    for (; j + 4 <= w; j += 4) {
+      int32_t c[4];
+      T v[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        c[u] = __ldg(cp + (int64_t)(j + u) * kSellC);
+        v[u] = __ldg(vp + (int64_t)(j + u) * kSellC);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = c[u] >= 0 ? gather_x(x, halo, c[u], nloc) : zero_of(T());
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c[u] >= 0) sum = add_t(sum, mul(v[u], xv[u]));
+    }
+    for (; j < w; ++j) {
+      const int32_t c = __ldg(cp + (int64_t)j * kSellC);
+      const T v = __ldg(vp + (int64_t)j * kSellC);
+      if (c >= 0) sum = add_t(sum, mul(v, gather_x(x, halo, c, nloc)));
+    }
+    const int64_t r = s * kSellC + lane;
+    if (r < n) {
+      const int64_t out = perm ? perm[r] : r;
+      const T xi = x[out];
+      const T yi = add_t(sum, scale_real(xi, sigma));
+      y[out] = yi;
+      dot += re_conj_mul(xi, yi);
+    }
+  }
+  const double t = block_sum(dot, scratch);
+  if (threadIdx.x == 0) pa[blockIdx.x] = t;
+}
+
 template <class T> struct CsrOp : OpBase {
   int64_t n_cols = 0;
   int64_t nnz = 0;
@@ -109,11 +238,48 @@ template <class T> struct CsrOp : OpBase {
   int lpr = 8;
   int stream_rows = 0;  // rows per CTA block of the stream kernel (0 = use the lanes-per-row kernel)
   int stream_cap = 0;   // products parked in shared memory per block
+  // row-sharded runs: halo exchange plan (empty for a single rank)
+  int64_t n_halo = 0, n_send = 0;
+  T* d_halo = nullptr;           // [n_halo] remote entries of x, grouped by owner
+  T* d_sendbuf = nullptr;        // [n_send] packed entries of the local block, grouped by requesting peer
+  int32_t* d_send_idx = nullptr; // [n_send] local indices to pack
+  std::vector<size_t> send_off, send_bytes, recv_off, recv_bytes;
+  // SELL-C-sigma storage (convert_to_sell releases the CSR arrays)
+  bool sell = false;
+  int sell_sigma = 1;
+  int64_t n_slices = 0, padded_nnz = 0;
+  int64_t* d_slice_ptr = nullptr;
+  int32_t* d_scol = nullptr;
+  T* d_sval = nullptr;
+  int32_t* d_perm = nullptr;  // null when rows are not sorted (sigma = 1)
 
   ~CsrOp() override {
+    if (d_slice_ptr) cudaFree(d_slice_ptr);
+    if (d_scol) cudaFree(d_scol);
+    if (d_sval) cudaFree(d_sval);
+    if (d_perm) cudaFree(d_perm);
     if (d_rowptr) cudaFree(d_rowptr);
     if (d_colidx) cudaFree(d_colidx);
     if (d_vals) cudaFree(d_vals);
+    if (d_halo) cudaFree(d_halo);
+    if (d_sendbuf) cudaFree(d_sendbuf);
+    if (d_send_idx) cudaFree(d_send_idx);
+  }
+  int32_t nloc32() const { return (int32_t)std::min<int64_t>(n_local, 0x7fffffff); }
+
+  // Bring the remote entries of x this block references into d_halo (no-op for a single rank).
+  int prepare(const void* x) override {
+    if (ctx->nranks == 1 || (n_halo == 0 && n_send == 0)) return LLZ_OK;
+    ProfScope ps(ctx, "halo", (double)(n_halo + n_send) * sizeof(T));
+    if (n_send > 0) {
+      const int64_t g = std::min<int64_t>((n_send + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 4);
+      k_pack<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, d_send_idx, d_sendbuf, n_send);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_pack: %s", cudaGetErrorString(e));
+      ctx->launches++;
+    }
+    return comm_exchange(ctx, (const char*)d_sendbuf, send_off.data(), send_bytes.data(), (char*)d_halo, recv_off.data(),
+                         recv_bytes.data());
   }
 
   template <class IDX, int LPR> int launch(const void* x, void* y, double sigma, double* pa, int* npa) {
@@ -122,7 +288,7 @@ template <class T> struct CsrOp : OpBase {
     int64_t g = std::min<int64_t>(blocks, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
     k_csr_spmv_dot<T, IDX, LPR><<<(int)g, kThreads, 0, ctx->stream>>>(
-        (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, (T*)y, n_local, (typename Num<T>::R)sigma, pa);
+        (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, d_halo, nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_csr_spmv_dot: %s", cudaGetErrorString(e));
@@ -150,8 +316,9 @@ template <class T> struct CsrOp : OpBase {
     const int64_t blocks = (n_local + stream_rows - 1) / stream_rows;
     int64_t g = std::min<int64_t>(blocks, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_csr_stream_dot<T, IDX><<<(int)g, kThreads, smem, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, (T*)y,
-                                                                     n_local, (typename Num<T>::R)sigma, pa, stream_rows, stream_cap);
+    k_csr_stream_dot<T, IDX><<<(int)g, kThreads, smem, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, d_halo,
+                                                                     nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa,
+                                                                     stream_rows, stream_cap);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_csr_stream_dot: %s", cudaGetErrorString(e));
@@ -159,65 +326,258 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
 
+  int launch_sell(const void* x, void* y, double sigma, double* pa, int* npa) {
+    int64_t g = std::min<int64_t>((n_slices + kWarps - 1) / kWarps, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
+    if (g < 1) g = 1;
+    k_sell_spmv_dot<T><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, d_halo, nloc32(), (T*)y,
+                                                            n_local, n_slices, (typename Num<T>::R)sigma, pa);
+    *npa = (int)g;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_sell_spmv_dot: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return LLZ_OK;
+  }
+
+  // Re-store the uploaded CSR arrays as SELL-32-sigma, entirely on the device (only the slice widths visit the host
+  // for the prefix sum).  sigma: 1 = keep the row order, 32..1024 (multiple of 32) = sort windows of sigma rows by
+  // length, 0 = pick (sort only if it saves more than 5 % of the padded storage).
+  template <class IDX> int convert_to_sell(int sigma) {
+    const int64_t n = n_local;
+    n_slices = (n + kSellC - 1) / kSellC;
+    int32_t* d_len = nullptr;
+    int32_t* d_width = nullptr;
+    LLZ_CUDA(dev_malloc(ctx, &d_len, sizeof(int32_t) * (size_t)n));
+    LLZ_CUDA(dev_malloc(ctx, &d_width, sizeof(int32_t) * (size_t)n_slices));
+    const int grid = (int)std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 8);
+    const int wgrid = (int)std::min<int64_t>((n_slices + kWarps - 1) / kWarps, (int64_t)ctx->num_sms * 8);
+    k_sell_rowlen<IDX><<<grid, kThreads, 0, ctx->stream>>>((const IDX*)d_rowptr, n, d_len);
+    std::vector<int32_t> width((size_t)n_slices);
+    auto widths_for = [&](const int32_t* perm, int64_t* total) -> int {
+      k_sell_width<<<wgrid, kThreads, 0, ctx->stream>>>(d_len, perm, n, n_slices, d_width);
+      LLZ_CUDA(cudaMemcpyAsync(width.data(), d_width, sizeof(int32_t) * (size_t)n_slices, cudaMemcpyDeviceToHost, ctx->stream));
+      LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+      int64_t t = 0;
+      for (int32_t w : width) t += (int64_t)w * kSellC;
+      *total = t;
+      return LLZ_OK;
+    };
+    auto sort_windows = [&](int sg) -> int {
+      if (!d_perm) LLZ_CUDA(dev_malloc(ctx, &d_perm, sizeof(int32_t) * (size_t)n));
+      const int64_t windows = (n + sg - 1) / sg;
+      k_sell_sort<<<(unsigned)windows, sg, sg * sizeof(int32_t), ctx->stream>>>(d_len, n, sg, d_perm);
+      return LLZ_OK;
+    };
+    int64_t total = 0;
+    int s = LLZ_OK;
+    if (sigma == 0) {
+      s = widths_for(nullptr, &total);
+      if (s == LLZ_OK && total > nnz + nnz / 20) {  // > 5 % padding: try sorting
+        int64_t sorted_total = 0;
+        s = sort_windows(256);
+        if (s == LLZ_OK) s = widths_for(d_perm, &sorted_total);
+        if (s == LLZ_OK && sorted_total + total / 20 < total) {
+          total = sorted_total;
+          sigma = 256;
+        } else if (s == LLZ_OK) {
+          cudaFree(d_perm);
+          d_perm = nullptr;
+          s = widths_for(nullptr, &total);
+          sigma = 1;
+        }
+      } else {
+        sigma = 1;
+      }
+    } else if (sigma == 1) {
+      s = widths_for(nullptr, &total);
+    } else {
+      s = sort_windows(sigma);
+      if (s == LLZ_OK) s = widths_for(d_perm, &total);
+    }
+    if (s != LLZ_OK) {
+      cudaFree(d_len);
+      cudaFree(d_width);
+      return s;
+    }
+    sell_sigma = sigma;
+    padded_nnz = total;
+    std::vector<int64_t> sp((size_t)n_slices + 1, 0);
+    for (int64_t i = 0; i < n_slices; ++i) sp[(size_t)i + 1] = sp[(size_t)i] + (int64_t)width[(size_t)i] * kSellC;
+    cudaError_t e = dev_malloc(ctx, &d_slice_ptr, sizeof(int64_t) * sp.size());
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_scol, std::max<size_t>(16, sizeof(int32_t) * (size_t)total));
+    if (e == cudaSuccess) e = dev_malloc(ctx, &d_sval, std::max<size_t>(16, sizeof(T) * (size_t)total));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_slice_ptr, sp.data(), sizeof(int64_t) * sp.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      k_sell_fill<T, IDX><<<wgrid, kThreads, 0, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, d_perm, d_slice_ptr, n, n_slices, d_scol, d_sval);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_len);
+    cudaFree(d_width);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "SELL conversion: %s", cudaGetErrorString(e));
+    cudaFree(d_rowptr);
+    cudaFree(d_colidx);
+    cudaFree(d_vals);
+    d_rowptr = nullptr;
+    d_colidx = nullptr;
+    d_vals = nullptr;
+    sell = true;
+    ctx->launches += 3;
+    bytes = padded_nnz * (int64_t)(sizeof(T) + 4) + (n_slices + 1) * 8 + (d_perm ? n * 4 : 0);
+    return LLZ_OK;
+  }
+
   int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa) override {
+    if (sell) return launch_sell(x, y, sigma, pa, npa);
     if (stream_rows > 0) return idx32 ? launch_stream<int32_t>(x, y, sigma, pa, npa) : launch_stream<int64_t>(x, y, sigma, pa, npa);
     return idx32 ? launch_lpr<int32_t>(x, y, sigma, pa, npa) : launch_lpr<int64_t>(x, y, sigma, pa, npa);
   }
 };
 
+// Row-sharded set-up: every rank learns the row ranges of the group, plans its halo (llz_halo_plan, host), tells each
+// owner which of its entries it needs, and receives the peers' requests.  Returns the column indices in the local
+// extended numbering.
 template <class T>
-static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, const int64_t* rowptr,
-                      const int32_t* colidx, const void* vals, int host_arrays, llz_op_t* out) {
+static int plan_sharded_csr(CsrOp<T>* op, int64_t row0, const int64_t* rowptr, const int32_t* colidx, std::vector<int32_t>& col_local) {
+  llz_ctx_t ctx = op->ctx;
+  const int G = ctx->nranks, me = ctx->rank;
+  const int64_t n_rows = op->n_local;
+  std::vector<int64_t> ranges((size_t)G * 2);
+  const int64_t mine[2] = {row0, n_rows};
+  LLZ_TRY(comm_allgather_host(ctx, mine, ranges.data(), sizeof(mine)));
+  std::vector<int64_t> bounds((size_t)G + 1, 0);
+  for (int r = 0; r < G; ++r) {
+    if (ranges[2 * r] != bounds[r])
+      return fail(LLZ_ERR_INVALID, "csr: the row blocks of the ranks must be contiguous and ordered by rank (rank %d starts at %lld, expected %lld)",
+                  r, (long long)ranges[2 * r], (long long)bounds[r]);
+    bounds[r + 1] = bounds[r] + ranges[2 * r + 1];
+  }
+  if (bounds[G] != op->n_cols) return fail(LLZ_ERR_INVALID, "csr: the row blocks cover %lld rows, the operator has %lld columns", (long long)bounds[G], (long long)op->n_cols);
+  const int64_t nnz = rowptr[n_rows];
+  col_local.resize((size_t)std::max<int64_t>(nnz, 1));
+  int64_t n_halo = 0;
+  std::vector<int64_t> need((size_t)G, 0);
+  LLZ_TRY(llz_halo_plan(n_rows, row0, rowptr, colidx, G, bounds.data(), nullptr, nullptr, 0, &n_halo, nullptr));
+  std::vector<int64_t> halo_cols((size_t)std::max<int64_t>(n_halo, 1));
+  LLZ_TRY(llz_halo_plan(n_rows, row0, rowptr, colidx, G, bounds.data(), col_local.data(), halo_cols.data(), n_halo, &n_halo, need.data()));
+  // need_all[q*G + p] = number of entries rank q needs from rank p
+  std::vector<int64_t> need_all((size_t)G * G);
+  LLZ_TRY(comm_allgather_host(ctx, need.data(), need_all.data(), sizeof(int64_t) * G));
+  op->n_halo = n_halo;
+  op->send_off.assign(G, 0);
+  op->send_bytes.assign(G, 0);
+  op->recv_off.assign(G, 0);
+  op->recv_bytes.assign(G, 0);
+  std::vector<size_t> req_off(G, 0), req_bytes(G, 0), got_off(G, 0), got_bytes(G, 0);
+  int64_t n_send = 0, h = 0;
+  for (int p = 0; p < G; ++p) {
+    const int64_t cnt_recv = need[p], cnt_send = need_all[(size_t)p * G + me];
+    op->recv_off[p] = (size_t)h * sizeof(T);
+    op->recv_bytes[p] = (size_t)cnt_recv * sizeof(T);
+    req_off[p] = (size_t)h * sizeof(int32_t);
+    req_bytes[p] = (size_t)cnt_recv * sizeof(int32_t);
+    h += cnt_recv;
+    op->send_off[p] = (size_t)n_send * sizeof(T);
+    op->send_bytes[p] = (size_t)cnt_send * sizeof(T);
+    got_off[p] = (size_t)n_send * sizeof(int32_t);
+    got_bytes[p] = (size_t)cnt_send * sizeof(int32_t);
+    n_send += cnt_send;
+  }
+  op->n_send = n_send;
+  // requests: for each halo entry the index inside its owner's block
+  std::vector<int32_t> req((size_t)std::max<int64_t>(n_halo, 1));
+  {
+    int owner = 0;
+    for (int64_t i = 0; i < n_halo; ++i) {
+      while (halo_cols[i] >= bounds[owner + 1]) ++owner;
+      req[(size_t)i] = (int32_t)(halo_cols[i] - bounds[owner]);
+    }
+  }
+  int32_t* d_req = nullptr;
+  LLZ_CUDA(dev_malloc(ctx, &d_req, sizeof(int32_t) * req.size()));
+  LLZ_CUDA(dev_malloc(ctx, &op->d_send_idx, sizeof(int32_t) * (size_t)std::max<int64_t>(n_send, 1)));
+  LLZ_CUDA(dev_malloc(ctx, &op->d_sendbuf, sizeof(T) * (size_t)std::max<int64_t>(n_send, 1)));
+  LLZ_CUDA(dev_malloc(ctx, &op->d_halo, sizeof(T) * (size_t)std::max<int64_t>(n_halo, 1)));
+  LLZ_CUDA(cudaMemcpyAsync(d_req, req.data(), sizeof(int32_t) * req.size(), cudaMemcpyHostToDevice, ctx->stream));
+  int s = comm_exchange(ctx, (const char*)d_req, req_off.data(), req_bytes.data(), (char*)op->d_send_idx, got_off.data(), got_bytes.data());
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_req);
+  if (s != LLZ_OK) return s;
+  if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "csr halo set-up: %s", cudaGetErrorString(e));
+  return LLZ_OK;
+}
+
+template <class T>
+static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr_in,
+                      const int32_t* colidx_in, const void* vals, int host_arrays, int sell_sigma, llz_op_t* out) {
   auto* op = new CsrOp<T>();
   op->ctx = ctx;
   op->dtype = dtype;
   op->n_local = n_rows;
+  op->n_global = n_cols;
+  op->row0 = row0;
   op->n_cols = n_cols;
-  const cudaMemcpyKind kind = host_arrays ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  // rowptr[n_rows] = nnz: fetch it to size the arrays
-  int64_t first = 0, last = 0;
-  if (host_arrays) {
-    first = rowptr[0];
-    last = rowptr[n_rows];
-  } else {
-    LLZ_CUDA(cudaMemcpy(&first, rowptr, sizeof(int64_t), cudaMemcpyDeviceToHost));
-    LLZ_CUDA(cudaMemcpy(&last, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  int s = LLZ_OK;
+  auto guard = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && s == LLZ_OK)
+      s = fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "csr %s: %s", what, cudaGetErrorString(e));
+  };
+  // the row pointers are always inspected on the host (kernel selection, 32-bit narrowing)
+  std::vector<int64_t> rp_host;
+  const int64_t* rowptr = rowptr_in;
+  if (!host_arrays) {
+    rp_host.resize((size_t)n_rows + 1);
+    guard(cudaMemcpy(rp_host.data(), rowptr_in, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyDeviceToHost), "rowptr fetch");
+    rowptr = rp_host.data();
   }
+  if (s != LLZ_OK) {
+    delete op;
+    return s;
+  }
+  const int64_t first = rowptr[0], last = rowptr[n_rows];
   if (first != 0 || last < 0) {
     delete op;
     return fail(LLZ_ERR_INVALID, "csr: rowptr must start at 0 (got %lld) and be non-decreasing", (long long)first);
   }
   op->nnz = last;
   op->idx32 = last < (int64_t)0x7fffffff;
-  int s = LLZ_OK;
-  auto guard = [&](cudaError_t e, const char* what) {
-    if (e != cudaSuccess && s == LLZ_OK)
-      s = fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "csr %s: %s", what, cudaGetErrorString(e));
-  };
-  guard(cudaMalloc(&op->d_colidx, std::max<size_t>(16, sizeof(int32_t) * (size_t)last)), "colidx alloc");
-  guard(cudaMalloc(&op->d_vals, std::max<size_t>(16, sizeof(T) * (size_t)last)), "vals alloc");
+
+  // row-sharded: rewrite the column indices to the local extended numbering and set up the halo exchange
+  const int32_t* colidx = colidx_in;
+  cudaMemcpyKind col_kind = host_arrays ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  std::vector<int32_t> col_host, col_local;
+  if (ctx->nranks > 1) {
+    if (!host_arrays) {
+      col_host.resize((size_t)std::max<int64_t>(last, 1));
+      guard(cudaMemcpy(col_host.data(), colidx_in, sizeof(int32_t) * (size_t)last, cudaMemcpyDeviceToHost), "colidx fetch");
+      colidx = col_host.data();
+    }
+    if (s == LLZ_OK) s = plan_sharded_csr<T>(op, row0, rowptr, colidx, col_local);
+    if (s != LLZ_OK) {
+      delete op;
+      return s;
+    }
+    colidx = col_local.data();
+    col_kind = cudaMemcpyHostToDevice;
+  }
+
+  const cudaMemcpyKind kind = host_arrays ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  guard(dev_malloc(ctx, &op->d_colidx, std::max<size_t>(16, sizeof(int32_t) * (size_t)last)), "colidx alloc");
+  guard(dev_malloc(ctx, &op->d_vals, std::max<size_t>(16, sizeof(T) * (size_t)last)), "vals alloc");
   if (s == LLZ_OK) {
-    guard(cudaMemcpyAsync(op->d_colidx, colidx, sizeof(int32_t) * (size_t)last, kind, ctx->stream), "colidx copy");
+    guard(cudaMemcpyAsync(op->d_colidx, colidx, sizeof(int32_t) * (size_t)last, col_kind, ctx->stream), "colidx copy");
     guard(cudaMemcpyAsync(op->d_vals, vals, sizeof(T) * (size_t)last, kind, ctx->stream), "vals copy");
   }
   if (s == LLZ_OK) {
     if (op->idx32) {
       // narrow the row pointers to 32 bits (halves their traffic: A_bytes = nnz*(s+4) + 4(n+1))
-      std::vector<int64_t> tmp;
-      const int64_t* src = rowptr;
-      if (!host_arrays) {
-        tmp.resize((size_t)n_rows + 1);
-        guard(cudaMemcpy(tmp.data(), rowptr, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyDeviceToHost), "rowptr fetch");
-        src = tmp.data();
-      }
       std::vector<int32_t> r32((size_t)n_rows + 1);
-      for (int64_t i = 0; i <= n_rows; ++i) r32[(size_t)i] = (int32_t)src[i];
-      guard(cudaMalloc(&op->d_rowptr, sizeof(int32_t) * (size_t)(n_rows + 1)), "rowptr alloc");
+      for (int64_t i = 0; i <= n_rows; ++i) r32[(size_t)i] = (int32_t)rowptr[i];
+      guard(dev_malloc(ctx, &op->d_rowptr, sizeof(int32_t) * (size_t)(n_rows + 1)), "rowptr alloc");
       if (s == LLZ_OK)
         guard(cudaMemcpy(op->d_rowptr, r32.data(), sizeof(int32_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice), "rowptr copy");
     } else {
-      guard(cudaMalloc(&op->d_rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)), "rowptr alloc");
-      if (s == LLZ_OK) guard(cudaMemcpyAsync(op->d_rowptr, rowptr, sizeof(int64_t) * (size_t)(n_rows + 1), kind, ctx->stream), "rowptr copy");
+      guard(dev_malloc(ctx, &op->d_rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)), "rowptr alloc");
+      if (s == LLZ_OK) guard(cudaMemcpyAsync(op->d_rowptr, rowptr, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice, ctx->stream), "rowptr copy");
     }
   }
   if (s == LLZ_OK) guard(cudaStreamSynchronize(ctx->stream), "sync");
@@ -228,22 +588,15 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
   // Stream kernel: largest power-of-two R <= 256 such that every block of R consecutive rows holds at most `cap`
   // non-zeros (cap bounded by ~40 KB of shared memory per CTA so several CTAs stay resident).
   {
-    std::vector<int64_t> tmp;
-    const int64_t* rp = rowptr;
-    if (!host_arrays) {
-      tmp.resize((size_t)n_rows + 1);
-      if (cudaMemcpy(tmp.data(), rowptr, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyDeviceToHost) != cudaSuccess) rp = nullptr;
-      else rp = tmp.data();
-    }
     const char* env = getenv("LLZ_SPMV");
     const bool want_stream = !(env && env[0] == 'v');
     const int cap_max = (int)((40 * 1024) / sizeof(T));
-    if (rp && want_stream) {
+    if (want_stream) {
       for (int R = 256; R >= 32; R /= 2) {
         int64_t worst = 0;
         for (int64_t r0 = 0; r0 < n_rows; r0 += R) {
           const int64_t r1 = std::min<int64_t>(n_rows, r0 + R);
-          worst = std::max(worst, rp[r1] - rp[r0]);
+          worst = std::max(worst, rowptr[r1] - rowptr[r0]);
         }
         if (worst <= cap_max) {
           op->stream_rows = R;
@@ -258,6 +611,13 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
   while (lpr < 32 && lpr < mean) lpr *= 2;
   op->lpr = lpr;
   op->bytes = last * (int64_t)(sizeof(T) + 4) + (n_rows + 1) * (op->idx32 ? 4 : 8);
+  if (sell_sigma >= 0) {
+    s = op->idx32 ? op->template convert_to_sell<int32_t>(sell_sigma) : op->template convert_to_sell<int64_t>(sell_sigma);
+    if (s != LLZ_OK) {
+      delete op;
+      return s;
+    }
+  }
   llz_op_t h = new llz_op_s();
   h->impl = op;
   *out = h;
@@ -294,21 +654,35 @@ using namespace llz;
 
 extern "C" {
 
-int llz_op_create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
-                      const int32_t* colidx, const void* vals, int host_arrays, llz_op_t* op) {
+static int create_sparse(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
+                         const int32_t* colidx, const void* vals, int host_arrays, int sell_sigma, llz_op_t* op) {
   if (!ctx || !rowptr || !colidx || !vals || !op || n_rows < 1 || n_cols < 1)
-    return fail(LLZ_ERR_INVALID, "op_create_csr: bad argument");
+    return fail(LLZ_ERR_INVALID, "op_create_csr/sell: bad argument");
   if (ctx->nranks == 1 && (row0 != 0 || n_rows != n_cols))
-    return fail(LLZ_ERR_INVALID, "op_create_csr: a single-rank operator must be square with row0 = 0");
-  if (ctx->nranks > 1) return fail(LLZ_ERR_UNSUPPORTED, "row-sharded CSR is not built yet");
+    return fail(LLZ_ERR_INVALID, "op_create_csr/sell: a single-rank operator must be square with row0 = 0");
+  if (ctx->nranks > 1 && (row0 < 0 || row0 + n_rows > n_cols))
+    return fail(LLZ_ERR_INVALID, "op_create_csr/sell: row block [%lld, %lld) outside the %lld rows of the operator", (long long)row0,
+                (long long)(row0 + n_rows), (long long)n_cols);
   LLZ_CUDA(cudaSetDevice(ctx->device));
   switch (dtype) {
-    case LLZ_F32: return create_csr<float>(ctx, dtype, n_rows, n_cols, rowptr, colidx, vals, host_arrays, op);
-    case LLZ_F64: return create_csr<double>(ctx, dtype, n_rows, n_cols, rowptr, colidx, vals, host_arrays, op);
-    case LLZ_C64: return create_csr<float2>(ctx, dtype, n_rows, n_cols, rowptr, colidx, vals, host_arrays, op);
-    case LLZ_C128: return create_csr<double2>(ctx, dtype, n_rows, n_cols, rowptr, colidx, vals, host_arrays, op);
+    case LLZ_F32: return create_csr<float>(ctx, dtype, n_rows, n_cols, row0, rowptr, colidx, vals, host_arrays, sell_sigma, op);
+    case LLZ_F64: return create_csr<double>(ctx, dtype, n_rows, n_cols, row0, rowptr, colidx, vals, host_arrays, sell_sigma, op);
+    case LLZ_C64: return create_csr<float2>(ctx, dtype, n_rows, n_cols, row0, rowptr, colidx, vals, host_arrays, sell_sigma, op);
+    case LLZ_C128: return create_csr<double2>(ctx, dtype, n_rows, n_cols, row0, rowptr, colidx, vals, host_arrays, sell_sigma, op);
   }
   return fail(LLZ_ERR_INVALID, "unknown dtype %d", dtype);
+}
+
+int llz_op_create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
+                      const int32_t* colidx, const void* vals, int host_arrays, llz_op_t* op) {
+  return create_sparse(ctx, dtype, n_rows, n_cols, row0, rowptr, colidx, vals, host_arrays, -1, op);
+}
+
+int llz_op_create_sell(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, int64_t row0, const int64_t* rowptr,
+                       const int32_t* colidx, const void* vals, int host_arrays, int sigma, llz_op_t* op) {
+  if (sigma < 0 || sigma > 1024 || (sigma > 1 && sigma % 32 != 0))
+    return fail(LLZ_ERR_INVALID, "op_create_sell: sigma must be 0 (auto), 1 (no sorting) or a multiple of 32 up to 1024 (got %d)", sigma);
+  return create_sparse(ctx, dtype, n_rows, n_cols, row0, rowptr, colidx, vals, host_arrays, sigma, op);
 }
 
 int llz_op_create_callback(llz_ctx_t ctx, int dtype, int64_t n_local, llz_apply_fn apply, void* user, int overwrites_y,
@@ -318,6 +692,20 @@ int llz_op_create_callback(llz_ctx_t ctx, int dtype, int64_t n_local, llz_apply_
   c->ctx = ctx;
   c->dtype = dtype;
   c->n_local = n_local;
+  c->n_global = n_local;
+  if (ctx->nranks > 1) {  // joined context: the callback owns a row block; the blocks are stacked in rank order
+    std::vector<int64_t> all((size_t)ctx->nranks);
+    int s = comm_allgather_host(ctx, &n_local, all.data(), sizeof(int64_t));
+    if (s != LLZ_OK) {
+      delete c;
+      return s;
+    }
+    c->n_global = 0;
+    for (int r = 0; r < ctx->nranks; ++r) {
+      if (r == ctx->rank) c->row0 = c->n_global;
+      c->n_global += all[(size_t)r];
+    }
+  }
   c->fn = apply;
   c->user = user;
   c->overwrites = overwrites_y != 0;
@@ -344,6 +732,14 @@ int llz_op_rows(llz_op_t op, int64_t* n) {
   return LLZ_OK;
 }
 
+int llz_op_shape(llz_op_t op, int64_t* n_local, int64_t* n_global, int64_t* row0) {
+  if (!op || !op->impl) return fail(LLZ_ERR_INVALID, "null");
+  if (n_local) *n_local = op->impl->n_local;
+  if (n_global) *n_global = op->impl->n_global;
+  if (row0) *row0 = op->impl->row0;
+  return LLZ_OK;
+}
+
 int llz_op_bytes(llz_op_t op, int64_t* bytes) {
   if (!op || !bytes) return fail(LLZ_ERR_INVALID, "null");
   *bytes = op->impl->bytes;
@@ -356,6 +752,7 @@ int llz_op_apply(llz_op_t op, llz_vec_t x, llz_vec_t y) {
   if (x->n != o->n_local || y->n != o->n_local || x->dtype != o->dtype || y->dtype != o->dtype)
     return fail(LLZ_ERR_INVALID, "op_apply: shape/dtype mismatch");
   int npa = 0;
+  LLZ_TRY(o->prepare(x->d));
   return o->apply_fused(x->d, y->d, 0.0, o->ctx->d_partials, &npa);
 }
 

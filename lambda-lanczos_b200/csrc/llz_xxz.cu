@@ -24,6 +24,8 @@ struct XxzParams {
   const uint32_t* rank_hi;  // [2^(L-half)]
   int64_t n;
   int64_t row0;        // first local row (row-sharded runs)
+  const void* x_all;   // row-sharded runs: the whole input vector, gathered before the launch (entries of the local
+                       // block are read from x itself); null for a single rank
 };
 
 __device__ __forceinline__ uint32_t xxz_unrank(int64_t idx, int L, int n_up) {
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(kThreads, 4)
   const uint32_t lo_mask = (1u << p.half) - 1u;
   const uint32_t wrap_flip = (1u << (p.L - 1)) | 1u;
   const int nbonds = p.periodic ? p.L : p.L - 1;
+  const T* __restrict__ xg = reinterpret_cast<const T*>(p.x_all);
   double dot = 0.0;
   const int64_t chunk = (int64_t)kThreads * ITEMS;
   for (int64_t base = (int64_t)blockIdx.x * chunk; base < p.n; base += (int64_t)gridDim.x * chunk) {
@@ -73,8 +76,9 @@ __global__ void __launch_bounds__(kThreads, 4)
         const int i = __ffs(d) - 1;
         d &= d - 1;
         const uint32_t t = s ^ ((i == p.L - 1) ? wrap_flip : (3u << i));
-        const int64_t j = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half)) - p.row0;
-        const T xv = __ldg(x + j);
+        const int64_t jg = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half));
+        const int64_t j = jg - p.row0;
+        const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + jg);
         acc = add_t(acc, xv);
       }
       const T xi = x[r];
@@ -93,9 +97,18 @@ struct XxzOpBase : OpBase {
   XxzParams prm;
   uint32_t* d_lo = nullptr;
   uint32_t* d_hi = nullptr;
+  void* d_xall = nullptr;  // row-sharded runs: gathered input vector (n_global elements)
+  std::vector<size_t> send_off, send_bytes, recv_off, recv_bytes;
   ~XxzOpBase() override {
     if (d_lo) cudaFree(d_lo);
     if (d_hi) cudaFree(d_hi);
+    if (d_xall) cudaFree(d_xall);
+  }
+  // Row-sharded: every rank sends its block of x to every peer (bit flips on high sites land anywhere in the sector).
+  int prepare(const void* x) override {
+    if (ctx->nranks == 1) return LLZ_OK;
+    ProfScope ps(ctx, "halo", (double)(n_global - n_local) * (double)dtype_size(dtype));
+    return comm_exchange(ctx, (const char*)x, send_off.data(), send_bytes.data(), (char*)d_xall, recv_off.data(), recv_bytes.data());
   }
 };
 
@@ -133,7 +146,6 @@ using namespace llz;
 extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, double jz, double jxy, int periodic, llz_op_t* out) {
   if (!ctx || !out || L < 2 || L > 32 || n_up < 0 || n_up > L || dtype_size(dtype) == 0)
     return fail(LLZ_ERR_INVALID, "op_create_xxz: need 2 <= L <= 32, 0 <= n_up <= L");
-  if (ctx->nranks > 1) return fail(LLZ_ERR_UNSUPPORTED, "row-sharded XXZ is not built yet");
   LLZ_CUDA(cudaSetDevice(ctx->device));
   init_binom();
   LLZ_CUDA(cudaMemcpyToSymbol(c_binom, host_binom, sizeof(host_binom)));
@@ -146,8 +158,15 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
   }
   op->ctx = ctx;
   op->dtype = dtype;
-  op->n_local = (int64_t)host_binom[L][n_up];
+  op->n_global = (int64_t)host_binom[L][n_up];
   op->bytes = 0;
+  {
+    const int s0 = llz_partition(op->n_global, ctx->rank, ctx->nranks, &op->row0, &op->n_local);
+    if (s0 != LLZ_OK || op->n_local < 1) {
+      delete op;
+      return s0 != LLZ_OK ? s0 : fail(LLZ_ERR_INVALID, "op_create_xxz: sector of %lld states is too small for %d ranks", (long long)host_binom[L][n_up], ctx->nranks);
+    }
+  }
   const int half = L / 2;
   // Lin tables: rank(s) = lo[s & lo_mask] + hi[s >> half].  The j-th set bit (1-based, counted from bit 0) at
   // position q contributes C(q, j); for the high half j continues from the number of set bits in the low half,
@@ -170,8 +189,8 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
     }
     hi[b] = (uint32_t)r;
   }
-  cudaError_t e = cudaMalloc(&op->d_lo, lo.size() * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&op->d_hi, hi.size() * sizeof(uint32_t));
+  cudaError_t e = dev_malloc(ctx, &op->d_lo, lo.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_hi, hi.size() * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpy(op->d_lo, lo.data(), lo.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(op->d_hi, hi.data(), hi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -187,7 +206,28 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
   op->prm.rank_lo = op->d_lo;
   op->prm.rank_hi = op->d_hi;
   op->prm.n = op->n_local;
-  op->prm.row0 = 0;
+  op->prm.row0 = op->row0;
+  op->prm.x_all = nullptr;
+  if (ctx->nranks > 1) {
+    const size_t es = dtype_size(dtype);
+    e = dev_malloc(ctx, &op->d_xall, (size_t)op->n_global * es);
+    if (e != cudaSuccess) {
+      delete op;
+      return fail(LLZ_ERR_OOM, "op_create_xxz: gathered input vector (%lld elements): %s", (long long)op->n_global, cudaGetErrorString(e));
+    }
+    op->prm.x_all = op->d_xall;
+    const int G = ctx->nranks;
+    op->send_off.assign(G, 0);
+    op->send_bytes.assign(G, (size_t)op->n_local * es);
+    op->recv_off.assign(G, 0);
+    op->recv_bytes.assign(G, 0);
+    for (int r = 0; r < G; ++r) {
+      int64_t r0 = 0, nl = 0;
+      llz_partition(op->n_global, r, G, &r0, &nl);
+      op->recv_off[r] = (size_t)r0 * es;
+      op->recv_bytes[r] = (size_t)nl * es;
+    }
+  }
   llz_op_t h = new llz_op_s();
   h->impl = op;
   *out = h;

@@ -73,6 +73,24 @@ class Context {
   static Context none() { return Context(Borrow{}); }
   llz_ctx_t get() const { return h_.get(); }
   void synchronize() const { check(llz_ctx_synchronize(h_.get()), "llz_ctx_synchronize"); }
+  // Join a row-sharded group: one process per GPU, `id128` = the blob of unique_id() made on rank 0 and handed to
+  // every rank by whatever transport the application has.  Afterwards vectors are local row blocks.
+  static std::vector<unsigned char> unique_id() {
+    std::vector<unsigned char> id(128);
+    check(llz_comm_unique_id(id.data()), "llz_comm_unique_id");
+    return id;
+  }
+  void join(int rank, int nranks, const void* id128) const { check(llz_ctx_join(h_.get(), rank, nranks, id128), "llz_ctx_join"); }
+  int rank() const {
+    int r = 0, n = 1;
+    check(llz_ctx_rank(h_.get(), &r, &n), "llz_ctx_rank");
+    return r;
+  }
+  int nranks() const {
+    int r = 0, n = 1;
+    check(llz_ctx_rank(h_.get(), &r, &n), "llz_ctx_rank");
+    return n;
+  }
   uint64_t launch_count() const {
     uint64_t c = 0;
     check(llz_ctx_launch_count(h_.get(), &c), "llz_ctx_launch_count");

@@ -22,6 +22,14 @@ class DeviceOperator {
           "llz_op_create_csr");
     return DeviceOperator(ctx, op, n);
   }
+  // SELL-32-sigma: same CSR input, re-stored on the device in sliced-ELL form (coalesced, barrier-free SpMV for
+  // stencil / lattice matrices); sigma = 0 picks whether to sort rows by length, 1 keeps the row order.
+  static DeviceOperator sell(const Context& ctx, size_t n, const int64_t* rowptr, const int32_t* colidx, const T* vals, int sigma = 0) {
+    llz_op_t op = nullptr;
+    check(llz_op_create_sell(ctx.get(), util::dtype_of<T>::value, (int64_t)n, (int64_t)n, 0, rowptr, colidx, vals, 1, sigma, &op),
+          "llz_op_create_sell");
+    return DeviceOperator(ctx, op, n);
+  }
   // COO triplets as in the reference's sparse sample (src/samples/sample2_sparse.cpp:14-47): duplicates are summed.
   static DeviceOperator coo(const Context& ctx, size_t n, const std::vector<size_t>& rows, const std::vector<size_t>& cols,
                             const std::vector<T>& vals) {
@@ -63,18 +71,27 @@ class DeviceOperator {
 
   // Non-owning view of an operator created through the C ABI.
   static DeviceOperator borrow(const Context& ctx, llz_op_t op) {
-    int64_t n = 0;
-    check(llz_op_rows(op, &n), "llz_op_rows");
     DeviceOperator d;
     d.ctx_ = ctx;
-    d.n_ = (size_t)n;
     d.h_.reset(op, [](llz_op_t) {});
+    d.read_shape();
     return d;
+  }
+  // Row block [row0, row0 + n_rows) of an n x n CSR matrix with GLOBAL column indices, for a context that joined a
+  // row-sharded group (Context::join); rowptr is local (starts at 0).
+  static DeviceOperator csr_rows(const Context& ctx, size_t n, size_t row0, size_t n_rows, const int64_t* rowptr,
+                                 const int32_t* colidx, const T* vals) {
+    llz_op_t op = nullptr;
+    check(llz_op_create_csr(ctx.get(), util::dtype_of<T>::value, (int64_t)n_rows, (int64_t)n, (int64_t)row0, rowptr, colidx, vals, 1, &op),
+          "llz_op_create_csr");
+    return DeviceOperator(ctx, op, n_rows);
   }
 
   bool valid() const { return (bool)h_; }
   llz_op_t get() const { return h_.get(); }
-  size_t rows() const { return n_; }
+  size_t rows() const { return n_; }                // rows of the local block (= vector length on this GPU)
+  size_t global_rows() const { return n_global_; }  // the reference's matrix_size
+  size_t row_offset() const { return row0_; }       // first global row of the local block
   const Context& context() const { return ctx_; }
   int64_t bytes() const {
     int64_t b = 0;
@@ -87,6 +104,14 @@ class DeviceOperator {
  private:
   DeviceOperator(const Context& ctx, llz_op_t op, size_t n) : ctx_(ctx), n_(n) {
     h_.reset(op, [](llz_op_t p) { llz_op_destroy(p); });
+    read_shape();
+  }
+  void read_shape() {
+    int64_t nl = 0, ng = 0, r0 = 0;
+    check(llz_op_shape(h_.get(), &nl, &ng, &r0), "llz_op_shape");
+    n_ = (size_t)nl;
+    n_global_ = (size_t)ng;
+    row0_ = (size_t)r0;
   }
   static int trampoline(void* user, const void* x, void* y, int64_t n, void* stream) {
     try {
@@ -99,7 +124,7 @@ class DeviceOperator {
   Context ctx_ = Context::none();
   std::shared_ptr<llz_op_s> h_;
   std::shared_ptr<DeviceFn> fn_;
-  size_t n_ = 0;
+  size_t n_ = 0, n_global_ = 0, row0_ = 0;
 };
 
 }  // namespace lambda_lanczos_b200

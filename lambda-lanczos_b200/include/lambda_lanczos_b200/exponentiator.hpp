@@ -41,8 +41,9 @@ class Exponentiator {
   // that feeds output back as input wants).  `output` may alias `input`.
   size_t run_device(const T& a, const DeviceVector<T>& input, DeviceVector<T>& output) const {
     const Context& ctx = mv_mul.context();
-    const size_t n = matrix_size;
-    if (input.size() != n) throw Error(LLZ_ERR_INVALID, "Exponentiator: input size differs from matrix_size");
+    const size_t n = mv_mul.rows();  // local block of a row-sharded run; == matrix_size on a single GPU
+    if (mv_mul.global_rows() != matrix_size) throw Error(LLZ_ERR_INVALID, "Exponentiator: mv_mul does not match matrix_size");
+    if (input.size() != n) throw Error(LLZ_ERR_INVALID, "Exponentiator: input size differs from the operator's (local) rows");
     if (!output.valid() || output.size() != n) output = DeviceVector<T>(ctx, n);
     const size_t want_cols = std::max<size_t>(2, max_iteration + 1);
     if (!work_.matches(util::dtype_of<T>::value, n, want_cols)) work_ = KrylovWorkspace(ctx, util::dtype_of<T>::value, n, want_cols);
@@ -113,12 +114,14 @@ class Exponentiator {
 
   // exponentiator.hpp:87 — host vectors in, host vector out (resized like the reference does, :163)
   size_t run(const T& a, const std::vector<T>& input, std::vector<T>& output) const {
+    // (row-sharded runs: `input` / `output` are this rank's row block)
     const Context& ctx = mv_mul.context();
-    if (input.size() != matrix_size) throw Error(LLZ_ERR_INVALID, "Exponentiator: input size differs from matrix_size");
-    DeviceVector<T> in(ctx, matrix_size), out(ctx, matrix_size);
+    const size_t n = mv_mul.rows();
+    if (input.size() != n) throw Error(LLZ_ERR_INVALID, "Exponentiator: input size differs from matrix_size");
+    DeviceVector<T> in(ctx, n), out(ctx, n);
     in.upload(input);
     const size_t it = run_device(a, in, out);
-    output.resize(matrix_size);
+    output.resize(n);
     out.download(output.data());
     return it;
   }
@@ -126,7 +129,7 @@ class Exponentiator {
   // exponentiator.hpp:175-210 — plain Taylor series summed backwards (kept as the reference keeps it: a cross-check)
   size_t taylor_run_device(const T& a, const DeviceVector<T>& input, DeviceVector<T>& output) {
     const Context& ctx = mv_mul.context();
-    const size_t n = matrix_size;
+    const size_t n = mv_mul.rows();
     if (!output.valid() || output.size() != n) output = DeviceVector<T>(ctx, n);
     if (a == T()) {  // :179-182
       check(llz_vec_copy(output.get(), input.get()), "llz_vec_copy");
@@ -157,10 +160,11 @@ class Exponentiator {
 
   size_t taylor_run(const T& a, const std::vector<T>& input, std::vector<T>& output) {
     const Context& ctx = mv_mul.context();
-    DeviceVector<T> in(ctx, matrix_size), out(ctx, matrix_size);
+    const size_t n = mv_mul.rows();
+    DeviceVector<T> in(ctx, n), out(ctx, n);
     in.upload(input);
     const size_t it = taylor_run_device(a, in, out);
-    output.resize(matrix_size);
+    output.resize(n);
     out.download(output.data());
     return it;
   }

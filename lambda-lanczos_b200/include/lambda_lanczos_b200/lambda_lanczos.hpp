@@ -148,6 +148,13 @@ class LambdaLanczos {
   int pipeline_depth = 1;                 // iterations the GPU may run ahead of the host convergence test
   int ritz_solver = 0;                    // 0: bisection on the extreme values, 1: full implicit QL every iteration
   double reorth_eta = 0.5;                // repeat the Gram-Schmidt pass when beta < reorth_eta * ||w'|| (DGKS)
+  // Row-sharded runs (the context joined a group): `matrix_size` stays the GLOBAL dimension and `init_vector` is asked
+  // for the whole start vector, of which this rank keeps rows [row_offset, row_offset + rows) — so a seeded
+  // initializer gives the same start vector for any number of GPUs.  Set `init_vector_local` to produce only the
+  // local block instead.  Either way, `start_local` (host pointer to the local block, n_local elements), when
+  // non-null, replaces both and is uploaded once per run().
+  std::function<void(std::vector<T>& vec)> init_vector_local;
+  const T* start_local = nullptr;
 
   LambdaLanczos(DeviceOperator<T> mv_mul, size_t matrix_size, bool find_maximum, size_t num_eigs)
       : mv_mul(std::move(mv_mul)), matrix_size(matrix_size), max_iteration(matrix_size), find_maximum(find_maximum), num_eigs(num_eigs) {}
@@ -157,8 +164,8 @@ class LambdaLanczos {
                        const std::vector<DeviceVector<T>>& orthogonalizeTo) {
     using clock = std::chrono::steady_clock;
     const Context& ctx = mv_mul.context();
-    const size_t n = matrix_size;
-    if (!mv_mul.valid() || mv_mul.rows() != n) throw Error(LLZ_ERR_INVALID, "LambdaLanczos: mv_mul does not match matrix_size");
+    if (!mv_mul.valid() || mv_mul.global_rows() != matrix_size) throw Error(LLZ_ERR_INVALID, "LambdaLanczos: mv_mul does not match matrix_size");
+    const size_t n = mv_mul.rows();  // local block; == matrix_size for a single GPU
     const size_t want_cols = std::max<size_t>(2, max_iteration + 1);
     if (!work_.matches(util::dtype_of<T>::value, n, want_cols)) work_ = KrylovWorkspace(ctx, util::dtype_of<T>::value, n, want_cols);
     llz_krylov_t kry = work_.get();
@@ -168,9 +175,22 @@ class LambdaLanczos {
     for (const auto& v : orthogonalizeTo) locked.push_back(v.get());
     check(llz_krylov_set_locked(kry, locked.data(), (int64_t)locked.size()), "llz_krylov_set_locked");
 
-    std::vector<T> start(n);
-    init_vector(start);  // :232
-    check(llz_krylov_begin(kry, start.data(), 1, nullptr), "llz_krylov_begin");
+    if (start_local) {  // :232 — the start vector is the same for every Lanczos run of this run(): keep it in HBM
+      if (!start_dev_.valid() || start_dev_.size() != n || start_dev_src_ != start_local) {
+        start_dev_ = DeviceVector<T>(ctx, n);
+        start_dev_.upload(start_local);
+        start_dev_src_ = start_local;
+      }
+      check(llz_krylov_begin(kry, start_dev_.device_ptr(), 0, nullptr), "llz_krylov_begin");
+    } else if (init_vector_local) {
+      std::vector<T> start(n);
+      init_vector_local(start);
+      check(llz_krylov_begin(kry, start.data(), 1, nullptr), "llz_krylov_begin");
+    } else {
+      std::vector<T> start(matrix_size);
+      init_vector(start);
+      check(llz_krylov_begin(kry, start.data() + mv_mul.row_offset(), 1, nullptr), "llz_krylov_begin");
+    }
 
     std::vector<double> alpha, beta;
     std::vector<double> evs, pevs;
@@ -282,8 +302,8 @@ class LambdaLanczos {
   size_t run_iteration(std::vector<real_t<T>>& eigvalues, std::vector<std::vector<T>>& eigvecs, size_t nroot, Iterable orthogonalizeTo) {
     std::vector<DeviceVector<T>> locked, out;
     for (auto it = orthogonalizeTo.cbegin(); it != orthogonalizeTo.cend(); ++it) {
-      locked.emplace_back(mv_mul.context(), matrix_size);
-      locked.back().upload(*it);
+      locked.emplace_back(mv_mul.context(), mv_mul.rows());
+      locked.back().upload(it->data() + (it->size() == matrix_size ? mv_mul.row_offset() : 0));
     }
     const size_t it = run_iteration(eigvalues, out, nroot, locked);
     eigvecs.clear();
@@ -316,6 +336,8 @@ class LambdaLanczos {
       eigenvectors.push_back(p.second);
     }
     mv_mul.context().synchronize();
+    start_dev_ = DeviceVector<T>();
+    start_dev_src_ = nullptr;
     stats_.runs = iter_counts_.size();
     stats_.kernel_launches = mv_mul.context().launch_count() - launches0;
     stats_.seconds_total = std::chrono::duration<double>(clock::now() - t0).count();
@@ -370,6 +392,8 @@ class LambdaLanczos {
   KrylovWorkspace work_;
   RunStatistics stats_;
   std::vector<double> last_alpha_, last_beta_;
+  DeviceVector<T> start_dev_;
+  const T* start_dev_src_ = nullptr;
 };
 
 }  // namespace lambda_lanczos_b200

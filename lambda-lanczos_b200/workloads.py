@@ -64,6 +64,36 @@ def laplacian2d_csr(nx: int, ny: int | None = None, dtype=np.float64):
     return rowptr, colidx, vals
 
 
+def partition(n: int, rank: int, nranks: int):
+    """Row block of ``rank`` in a group of ``nranks``: (row0, n_local) with row0 = n*rank // nranks — the same
+    arithmetic as ``llz_partition`` (csrc/llz_halo.cpp)."""
+    a = n * rank // nranks
+    b = n * (rank + 1) // nranks
+    return a, b - a
+
+
+def csr_row_block(rowptr, colidx, vals, row0: int, n_rows: int):
+    """Rows [row0, row0 + n_rows) of a CSR matrix: local row pointers (starting at 0), GLOBAL column indices."""
+    lo, hi = int(rowptr[row0]), int(rowptr[row0 + n_rows])
+    return (rowptr[row0:row0 + n_rows + 1] - lo).astype(np.int64), colidx[lo:hi], vals[lo:hi]
+
+
+def laplacian2d_csr_rows(nx: int, row0: int, n_rows: int, ny: int | None = None, dtype=np.float64):
+    """Rows [row0, row0 + n_rows) of ``laplacian2d_csr(nx, ny)`` built directly (a rank of a row-sharded run never
+    materialises the whole matrix); bit-identical to slicing the full matrix."""
+    ny = nx if ny is None else ny
+    idx = np.arange(row0, row0 + n_rows, dtype=np.int64)
+    x = idx % nx
+    y = idx // nx
+    cand_col = np.stack([idx - nx, idx - 1, idx, idx + 1, idx + nx], axis=1)
+    cand_ok = np.stack([y > 0, x > 0, np.ones(n_rows, bool), x < nx - 1, y < ny - 1], axis=1)
+    cand_val = np.array([-1.0, -1.0, 4.0, -1.0, -1.0])
+    counts = cand_ok.sum(axis=1)
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    return rowptr, cand_col[cand_ok].astype(np.int32), np.broadcast_to(cand_val, (n_rows, 5))[cand_ok].astype(dtype)
+
+
 def laplacian2d_exact(nx: int, ny: int | None = None, count: int = 4) -> np.ndarray:
     ny = nx if ny is None else ny
     p = np.arange(1, nx + 1)

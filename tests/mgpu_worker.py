@@ -1,0 +1,246 @@
+"""Worker of the row-sharded tests: run under torch.distributed.run with N processes.
+
+    --mode cpu   (gloo, no GPU):  the host-side sharding logic — llz_partition, llz_halo_plan and the exchange protocol
+                 of the sharded CSR operator (requests to owners -> packed entries back), replayed with numpy + gloo and
+                 checked against the unsharded matrix-vector product.
+    --mode gpu   (nccl, one GPU per rank): the CUDA path through the C ABI — sharded CSR (halo exchange), sharded
+                 matrix-free XXZ (gathered input), LambdaLanczos and Exponentiator on row blocks — against the same
+                 problem solved by an un-joined single-GPU context on rank 0's device.
+Prints "MGPU_OK rank=<r>" on success; any assertion kills the job.
+"""
+import argparse
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+i64 = C.c_int64
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def halo_plan(lib, rowptr, colidx, row0, bounds):
+    """llz_halo_plan through ctypes -> (colidx_local, halo_cols, per_owner)."""
+    n_rows = rowptr.size - 1
+    G = bounds.size - 1
+    n_halo = i64(0)
+    assert lib.llz_halo_plan(i64(n_rows), i64(row0), ptr(rowptr), ptr(colidx), C.c_int(G), ptr(bounds), None, None, i64(0),
+                             C.byref(n_halo), None) == 0
+    col_local = np.zeros(max(colidx.size, 1), dtype=np.int32)
+    halo = np.zeros(max(n_halo.value, 1), dtype=np.int64)
+    per_owner = np.zeros(G, dtype=np.int64)
+    assert lib.llz_halo_plan(i64(n_rows), i64(row0), ptr(rowptr), ptr(colidx), C.c_int(G), ptr(bounds), ptr(col_local), ptr(halo),
+                             i64(halo.size), C.byref(n_halo), ptr(per_owner)) == 0
+    return col_local[:colidx.size], halo[:n_halo.value], per_owner
+
+
+def run_cpu(rank, world):
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo")
+    pkg = entry.load_package()
+    wl = importlib.import_module("lambda_lanczos_b200.workloads")
+    lib = pkg.lib()
+    for name, full in (("laplacian", wl.laplacian2d_csr(23, 17)), ("random", wl.random_symmetric_csr(501, 6)),
+                       ("xxz", wl.xxz_csr(10))):
+        n = full[0].size - 1
+        bounds = np.array([wl.partition(n, r, world)[0] for r in range(world)] + [n], dtype=np.int64)
+        r0c, nlc = i64(0), i64(0)
+        assert lib.llz_partition(i64(n), C.c_int(rank), C.c_int(world), C.byref(r0c), C.byref(nlc)) == 0
+        row0, n_local = wl.partition(n, rank, world)
+        assert (r0c.value, nlc.value) == (row0, n_local)
+        rp, ci, va = wl.csr_row_block(*full, row0, n_local)
+        rp, ci = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(ci, dtype=np.int32)
+        col_local, halo_cols, per_owner = halo_plan(lib, rp, ci, row0, bounds)
+        # the plan: sorted unique remote columns, grouped by owner, local numbering consistent
+        remote = np.unique(ci[(ci < row0) | (ci >= row0 + n_local)])
+        assert np.array_equal(halo_cols, remote), name
+        assert per_owner[rank] == 0 and per_owner.sum() == remote.size
+        ext = np.concatenate([np.arange(row0, row0 + n_local), halo_cols])
+        assert np.array_equal(ext[col_local], ci), name
+        # exchange protocol of plan_sharded_csr / CsrOp::prepare (csrc/llz_ops.cu), replayed over gloo
+        need_all = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(need_all, torch.from_numpy(per_owner.copy()))
+        need_all = np.stack([t.numpy() for t in need_all])  # need_all[q, p] = entries q needs from p
+        owner_of = np.searchsorted(bounds, halo_cols, side="right") - 1
+        requests = [torch.from_numpy((halo_cols[owner_of == p] - bounds[p]).astype(np.int64)) for p in range(world)]
+        incoming = [torch.zeros(int(need_all[q, rank]), dtype=torch.int64) for q in range(world)]
+        _all_to_all(dist, incoming, requests, rank, world)
+        x_full = np.random.RandomState(7).uniform(-1, 1, n)
+        x_local = x_full[row0:row0 + n_local]
+        packed = [torch.from_numpy(x_local[idx.numpy()].copy()) for idx in incoming]
+        halo_parts = [torch.zeros(int(per_owner[p]), dtype=torch.float64) for p in range(world)]
+        _all_to_all(dist, halo_parts, packed, rank, world)
+        halo = np.concatenate([t.numpy() for t in halo_parts])
+        assert np.array_equal(halo, x_full[halo_cols]), name
+        x_ext = np.concatenate([x_local, halo])
+        y_local = _spmv(rp, col_local, va, x_ext)
+        y_full = wl.csr_matvec(*full, x_full)
+        assert np.allclose(y_local, y_full[row0:row0 + n_local], rtol=0, atol=1e-13), name
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"MGPU_OK rank={rank}", flush=True)
+
+
+def _all_to_all(dist, outputs, inputs, rank, world):
+    """gloo has no all_to_all: pairwise isend/irecv."""
+    reqs = []
+    for p in range(world):
+        if p == rank:
+            outputs[p].copy_(inputs[p])
+            continue
+        if inputs[p].numel():
+            reqs.append(dist.isend(inputs[p], dst=p))
+        if outputs[p].numel():
+            reqs.append(dist.irecv(outputs[p], src=p))
+    for r in reqs:
+        r.wait()
+
+
+def _spmv(rowptr, colidx, vals, x):
+    y = np.zeros(rowptr.size - 1, dtype=np.result_type(vals.dtype, x.dtype))
+    prod = vals * x[colidx]
+    np.add.at(y, np.repeat(np.arange(rowptr.size - 1), np.diff(rowptr)), prod)
+    return y
+
+
+def gather_blocks(dist, torch, local: np.ndarray, world: int, sizes):
+    """All ranks' row blocks concatenated (uneven sizes) via NCCL on device tensors."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    is_c = local.dtype.kind == "c"
+    raw = local.view(np.float64 if local.dtype.itemsize // (2 if is_c else 1) == 8 else np.float32)
+    mult = raw.size // max(local.size, 1) if local.size else (2 if is_c else 1)
+    parts = [torch.zeros(int(s) * mult, dtype=torch.from_numpy(raw[:0].copy()).dtype, device=dev) for s in sizes]
+    _gatherv(dist, torch, parts, raw, dev)
+    return np.concatenate([p.cpu().numpy() for p in parts]).view(local.dtype)
+
+
+def _gatherv(dist, torch, parts, raw, dev):
+    mine = torch.from_numpy(raw.copy()).to(dev)
+    for r in range(len(parts)):
+        if r == dist.get_rank():
+            parts[r].copy_(mine)
+        dist.broadcast(parts[r], src=r)
+
+
+def run_gpu(rank, world):
+    import torch
+    import torch.distributed as dist
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = entry.load_package()
+    wl = importlib.import_module("lambda_lanczos_b200.workloads")
+    ctx = pkg.Context(local_rank)
+    blob = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    if rank == 0:
+        blob.copy_(torch.frombuffer(bytearray(pkg.Context.unique_id()), dtype=torch.uint8))
+    dist.broadcast(blob, src=0)
+    ctx.join(rank, world, blob.cpu().numpy().tobytes())
+    solo = pkg.Context(local_rank)  # un-joined context: the single-GPU answer to compare with
+
+    def sizes_of(n):
+        return [wl.partition(n, r, world)[1] for r in range(world)]
+
+    # ---- 1. sharded CSR SpMV (halo exchange) and sharded XXZ (gathered input) against the unsharded apply ----
+    for name, full, dtype in (("laplacian", wl.laplacian2d_csr(61, 47), np.float64), ("random", wl.random_symmetric_csr(3001, 8), np.float64),
+                              ("peierls", wl.peierls_csr(24, 20), np.complex128), ("random32", wl.random_symmetric_csr(2000, 5, dtype=np.float32), np.float32)):
+        n = full[0].size - 1
+        row0, nl = wl.partition(n, rank, world)
+        op = pkg.Operator.csr(ctx, *wl.csr_row_block(*full, row0, nl), row0=row0, n_cols=n)
+        assert (op.n, op.n_global, op.row0) == (nl, n, row0)
+        x = wl.start_vector(n, dtype, seed=3)
+        y_local = op.matvec(x[row0:row0 + nl])
+        y_ref = pkg.Operator.csr(solo, *full).matvec(x)
+        assert np.array_equal(y_local, y_ref[row0:row0 + nl]), name  # same summation order per row: bit-identical
+    for L, dtype in ((12, np.float64), (14, np.complex128)):
+        opx = pkg.Operator.xxz(ctx, L, dtype=dtype)
+        n = opx.n_global
+        row0, nl = wl.partition(n, rank, world)
+        assert (opx.n, opx.row0) == (nl, row0)
+        x = wl.start_vector(n, dtype, seed=5)
+        y_local = opx.matvec(x[row0:row0 + nl])
+        y_ref = pkg.Operator.xxz(solo, L, dtype=dtype).matvec(x)
+        assert np.array_equal(y_local, y_ref[row0:row0 + nl]), L
+
+    # ---- 2. LambdaLanczos on row blocks vs single GPU: eigenvalues 1e-10, overlap 1-1e-9, iteration counts ----
+    cases = [("random max", wl.random_symmetric_csr(20000, 8), True, 1, {}),
+             ("laplacian 4 smallest", wl.laplacian2d_csr(48), False, 4, {}),
+             ("peierls 2 lowest", wl.peierls_csr(20, 20, flux=0.05, trap=0.3), False, 2, {})]
+    for name, full, find_max, k, extra in cases:
+        n = full[0].size - 1
+        dtype = full[2].dtype
+        row0, nl = wl.partition(n, rank, world)
+        start = wl.start_vector(n, dtype)
+        eng = pkg.LambdaLanczos(pkg.Operator.csr(ctx, *wl.csr_row_block(*full, row0, nl), row0=row0, n_cols=n), n, find_max, k)
+        eng.init_vector = start[row0:row0 + nl]
+        ev, vec = eng.run()
+        ref = pkg.LambdaLanczos(pkg.Operator.csr(solo, *full), n, find_max, k)
+        ref.init_vector = start
+        ev_ref, vec_ref = ref.run()
+        assert np.allclose(ev, ev_ref, rtol=1e-10, atol=0), (name, ev, ev_ref)
+        full_vecs = np.stack([gather_blocks(dist, torch, np.ascontiguousarray(vec[i]), world, sizes_of(n)) for i in range(len(ev))])
+        gaps_ok = True
+        for i in range(len(ev)):
+            ov = abs(np.vdot(vec_ref[i], full_vecs[i]))
+            res = np.linalg.norm(wl.csr_matvec(*full, full_vecs[i]) - ev[i] * full_vecs[i])
+            res_ref = np.linalg.norm(wl.csr_matvec(*full, vec_ref[i]) - ev_ref[i] * vec_ref[i])
+            degenerate = any(abs(ev_ref[i] - ev_ref[j]) < 1e-9 * max(1, abs(ev_ref[i])) for j in range(len(ev)) if j != i)
+            if not degenerate:
+                assert 1 - ov < 1e-9, (name, i, ov)
+            assert res < max(10 * res_ref, 1e-9), (name, i, res, res_ref)
+        if rank == 0:
+            print(f"  {name}: iterations sharded {eng.getIterationCounts()} single {ref.getIterationCounts()} eigenvalues {ev}", flush=True)
+
+    # ---- 3. XXZ ground state (config 4 at small L) and Exponentiator (config 5) on row blocks ----
+    L = 16
+    opx = pkg.Operator.xxz(ctx, L)
+    n = opx.n_global
+    row0, nl = wl.partition(n, rank, world)
+    start = wl.start_vector(n)
+    eng = pkg.LambdaLanczos(opx, n, False, 1)
+    eng.init_vector = start[row0:row0 + nl]
+    ev, vec = eng.run()
+    assert abs(ev[0] - (-7.1422963606168)) < 1e-10 * 7.2, ev  # SURVEY.md §8d probe value
+    ref = pkg.LambdaLanczos(pkg.Operator.xxz(solo, L), n, False, 1)
+    ref.init_vector = start
+    ev_ref, vec_ref = ref.run()
+    g = gather_blocks(dist, torch, np.ascontiguousarray(vec[0]), world, sizes_of(n))
+    assert abs(ev[0] - ev_ref[0]) <= 1e-10 * abs(ev_ref[0]) and 1 - abs(np.vdot(vec_ref[0], g)) < 1e-9
+
+    L = 14
+    opc = pkg.Operator.xxz(ctx, L, dtype=np.complex128)
+    n = opc.n_global
+    row0, nl = wl.partition(n, rank, world)
+    psi = wl.neel_state(L)
+    ex = pkg.Exponentiator(opc, n)
+    ex_ref = pkg.Exponentiator(pkg.Operator.xxz(solo, L, dtype=np.complex128), n)
+    cur, cur_ref = psi[row0:row0 + nl].copy(), psi.copy()
+    for step in range(3):
+        it, cur = ex.run(-0.1j, cur)
+        it_ref, cur_ref = ex_ref.run(-0.1j, cur_ref)
+        assert it == it_ref, (it, it_ref)
+    g = gather_blocks(dist, torch, np.ascontiguousarray(cur), world, sizes_of(n))
+    assert np.linalg.norm(g - cur_ref) <= 1e-10 * np.linalg.norm(cur_ref)
+    ctx.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"MGPU_OK rank={rank}", flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", choices=["cpu", "gpu"], required=True)
+    a = ap.parse_args()
+    r, w = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    (run_cpu if a.mode == "cpu" else run_gpu)(r, w)

@@ -95,6 +95,95 @@ def test_csr_operator_matches_numpy(pkg, ctx, wl, dtype):
         assert op.bytes() > 0
 
 
+def ragged_csr(n, seed=0, dtype=np.float64):
+    """Rows of wildly different lengths, including empty ones and one very long row."""
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(seed)
+    lens = rs.choice([0, 1, 2, 3, 5, 9, 40], size=n, p=[0.1, 0.2, 0.2, 0.2, 0.15, 0.1, 0.05])
+    lens[n // 2] = min(n, 700)
+    rows = np.repeat(np.arange(n), lens)
+    cols = rs.randint(0, n, size=rows.size)
+    vals = rs.uniform(-1, 1, size=rows.size)
+    a = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+    a.sum_duplicates()
+    a.sort_indices()
+    v = a.data.astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        v = v * np.exp(1j * rs.uniform(0, 6, size=v.size)).astype(dtype)
+    return a.indptr.astype(np.int64), a.indices.astype(np.int32), v
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("sigma", [0, 1, 32, 256, 1024])
+def test_sell_operator_is_bit_identical_to_csr(pkg, ctx, wl, dtype, sigma):
+    """SELL-C-sigma keeps the per-row summation order of CSR: y must match bit for bit, whatever the slicing/sorting,
+    for regular stencils, random matrices and ragged ones (empty rows, one 700-entry row, n not a multiple of 32)."""
+    cases = [wl.laplacian2d_csr(37, 41, dtype=np.float64), wl.random_symmetric_csr(5003), ragged_csr(3001, 1), ragged_csr(31, 2), ragged_csr(1, 3)]
+    if np.dtype(dtype).kind == "c":
+        cases.append(wl.peierls_csr(23, 19))
+        cases.append(ragged_csr(2050, 4, np.complex128))
+    for csr in cases:
+        csr = (csr[0], csr[1], csr[2].astype(dtype))
+        n = csr[0].size - 1
+        x = rnd(np.random.RandomState(1), n, dtype)
+        y_csr = pkg.Operator.csr(ctx, *csr).matvec(x)
+        op = pkg.Operator.sell(ctx, *csr, sigma=sigma)
+        y = op.matvec(x)
+        assert np.array_equal(y, y_csr), (n, sigma)
+        assert op.bytes() > 0
+    # padding entries are skipped, never multiplied: an Inf in x only reaches the rows that reference it
+    csr = ragged_csr(3001, 1, dtype)
+    x = rnd(np.random.RandomState(2), 3001, dtype)
+    x[17] = np.inf
+    y = pkg.Operator.sell(ctx, *csr, sigma=sigma).matvec(x)
+    touched = np.zeros(3001, bool)
+    touched[np.repeat(np.arange(3001), np.diff(csr[0]))[csr[1] == 17]] = True
+    assert np.all(np.isfinite(y[~touched]))
+
+
+def test_sell_rejects_bad_sigma(pkg, ctx, wl):
+    with pytest.raises(pkg.LlzError) as e:
+        pkg.Operator.sell(ctx, *wl.laplacian2d_csr(8), sigma=48)
+    assert e.value.status == 1
+
+
+def test_lanczos_on_sell_matches_csr_run(pkg, ctx, wl):
+    """Same operator in both formats => identical Lanczos run (y is bit-identical; alpha's partial sums are grouped
+    differently, so scalars agree to rounding and eigenpairs to the parity tolerance)."""
+    csr = wl.laplacian2d_csr(48)
+    n = 48 * 48
+    out = []
+    for make in (pkg.Operator.csr, pkg.Operator.sell):
+        eng = pkg.LambdaLanczos(make(ctx, *csr), n, False, 4)
+        eng.init_vector = wl.start_vector(n)
+        ev, vec = eng.run()
+        out.append((ev, vec, eng.getIterationCounts()))
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-10, atol=0)
+    assert np.allclose(out[1][0], wl.laplacian2d_exact(48, count=4), rtol=1e-10, atol=0)
+    assert abs(abs(np.vdot(out[0][1][0], out[1][1][0])) - 1) < 1e-9
+
+
+def test_workspace_cache_reuse_is_invisible(pkg, ctx, wl):
+    """The context revives the Krylov workspace and vector buffers of the previous run: results are bit-identical to a
+    run on released caches, and different shapes in between do not confuse it."""
+    csr = wl.random_symmetric_csr(20000)
+    runs = []
+    for i in range(3):
+        if i == 1:
+            ctx.release_cache()
+        if i == 2:  # a run of another shape and dtype in between
+            e2 = pkg.LambdaLanczos(pkg.Operator.csr(ctx, *wl.peierls_csr(12, 12)), 144, False, 2)
+            e2.init_vector = wl.start_vector(144, np.complex128)
+            e2.run()
+        eng = pkg.LambdaLanczos(pkg.Operator.csr(ctx, *csr), 20000, True, 1)
+        eng.init_vector = wl.start_vector(20000)
+        ev, vec = eng.run()
+        runs.append((ev, vec, eng.getIterationCounts()))
+    for ev, vec, it in runs[1:]:
+        assert np.array_equal(ev, runs[0][0]) and np.array_equal(vec, runs[0][1]) and it == runs[0][2]
+
+
 @pytest.mark.parametrize("L,n_up,pbc", [(4, 2, True), (8, 4, True), (10, 3, False), (14, 7, True), (16, 8, True), (13, 6, True)])
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_xxz_matrix_free_matches_explicit_matrix(pkg, ctx, wl, L, n_up, pbc, dtype):
