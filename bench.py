@@ -274,7 +274,7 @@ def run_ours(args, rank, world):
     # device time of the K steps on the launching stream (host control included), max over the ranks
     dt = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     launches = ctx.launch_count() - launches0
-    prof = {name: ctx.profile_read(name) for name in ("spmv", "halo", "project", "reduce", "update", "scale", "combine", "dot")}
+    prof = {name: ctx.profile_read(name) for name in ("spmv", "halo", "exchange", "project", "reduce", "update", "scale", "combine", "dot")}
     ctx.profile(False)
     clocks = sampler.stop()
     value = iters / dt
@@ -322,6 +322,7 @@ def run_ours(args, rank, world):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "iterations_per_step": sum(counts), "lanczos_runs_per_step": len(counts),
                        "parallelism": f"rows{world}" if world > 1 else "single GPU",
+                       "scalar_exchange": ("peer-memory channels (NVLink stores from the kernels)" if ctx.peer_channels() else "NCCL all-reduce") if world > 1 else None,
                        "operator_storage": "CSR input re-stored on the device as SELL-32-sigma" if args.format == "sell" else "CSR",
                        "operator_bytes_per_gpu": int(a_bytes),
                        "l2": "inputs (basis of up to %d x %d MB per GPU) far exceed the 126 MB L2" % (args.max_iteration + 1, n_local * 8 // 1000000),

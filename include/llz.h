@@ -90,6 +90,10 @@ int llz_ctx_profile_read(llz_ctx_t ctx, const char* name, double* ms, int64_t* l
 int llz_comm_unique_id(void* id128);
 int llz_ctx_join(llz_ctx_t ctx, int rank, int nranks, const void* id128);
 int llz_ctx_rank(llz_ctx_t ctx, int* rank, int* nranks);
+/* *enabled = 1 when the joined group exchanges the per-iteration scalars (alpha, the projection coefficients, beta^2)
+ * through CUDA-IPC mapped peer memory written from inside the producing kernels (csrc/llz_peer.cuh), 0 when it uses
+ * NCCL all-reduces (single rank, IPC unavailable, or LLZ_P2P=0 in the environment). */
+int llz_ctx_peer_channels(llz_ctx_t ctx, int* enabled);
 /* The row partition every built-in operator and the bench use: rank r owns [n*r/G, n*(r+1)/G).  Pure host arithmetic. */
 int llz_partition(int64_t n_global, int rank, int nranks, int64_t* row0, int64_t* n_local);
 /* Host-side halo planning for the local row block of a CSR matrix with GLOBAL column indices (no GPU involved):

@@ -105,6 +105,12 @@ class Context:
         _check(lib().llz_ctx_join(self.h, C.c_int(rank), C.c_int(nranks), buf), "llz_ctx_join")
         self.rank, self.nranks = rank, nranks
 
+    def peer_channels(self) -> bool:
+        """True when the per-iteration scalars travel through peer memory (NVLink stores from inside the kernels)."""
+        e = C.c_int(0)
+        _check(lib().llz_ctx_peer_channels(self.h, C.byref(e)), "llz_ctx_peer_channels")
+        return bool(e.value)
+
     def synchronize(self):
         _check(lib().llz_ctx_synchronize(self.h), "llz_ctx_synchronize")
 

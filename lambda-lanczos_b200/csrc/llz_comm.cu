@@ -5,28 +5,81 @@
 // Per Lanczos iteration a joined context issues: one halo exchange before the SpMV (only the remote entries the local
 // rows reference, ncclSend/ncclRecv grouped), one all-reduce of the packed projection coefficients, and all-reduces of
 // the alpha / beta^2 scalars.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the library itself is bound at run time (see NcclApi)
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "llz_launch.hpp"
+#include "llz_peer.cuh"
 
 namespace llz {
 
+// NCCL is bound lazily, the first time a context joins a group: single-GPU processes never load it, and a process
+// that already holds a copy (e.g. PyTorch's bundled libnccl.so.2) shares that copy instead of pulling a second,
+// possibly older one under the same SONAME.
+struct NcclApi {
+  bool ok = false;
+  const char* why = "";
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // a copy this process already uses
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) {
+    api.why = "libnccl.so.2 not found";
+    return api;
+  }
+  auto get = [&](const char* name, void** fn) {
+    *fn = dlsym(h, name);
+    return *fn != nullptr;
+  };
+  api.ok = get("ncclGetUniqueId", (void**)&api.GetUniqueId) && get("ncclCommInitRank", (void**)&api.CommInitRank) &&
+           get("ncclCommDestroy", (void**)&api.CommDestroy) && get("ncclAllReduce", (void**)&api.AllReduce) &&
+           get("ncclAllGather", (void**)&api.AllGather) && get("ncclSend", (void**)&api.Send) && get("ncclRecv", (void**)&api.Recv) &&
+           get("ncclGroupStart", (void**)&api.GroupStart) && get("ncclGroupEnd", (void**)&api.GroupEnd) &&
+           get("ncclGetErrorString", (void**)&api.GetErrorString);
+  if (!api.ok) api.why = "libnccl.so.2 lacks an expected symbol";
+  return api;
+}
+
 struct Comm {
   ncclComm_t nccl = nullptr;
+  // peer-memory channels for the per-iteration scalar reductions (llz_peer.cuh); G == 0 when unavailable
+  void* p2p_local = nullptr;
+  void* p2p_peer[kMaxRanks] = {};
+  PeerChannel ch[3];
+  unsigned long long seq[3] = {0, 0, 0};
+  unsigned int* ticket = nullptr;
 };
 
 #define LLZ_NCCL(expr)                                                                                       \
   do {                                                                                                       \
     ncclResult_t r__ = (expr);                                                                               \
-    if (r__ != ncclSuccess) return ::llz::fail(LLZ_ERR_COMM, "%s: %s", #expr, ncclGetErrorString(r__));      \
+    if (r__ != ncclSuccess) return ::llz::fail(LLZ_ERR_COMM, "%s: %s", #expr, nccl().GetErrorString(r__));   \
   } while (0)
 
 int comm_allreduce_sum(llz_ctx_t ctx, double* d, int count) {
   if (ctx->nranks == 1 || count <= 0) return LLZ_OK;
-  LLZ_NCCL(ncclAllReduce(d, d, (size_t)count, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
+  LLZ_NCCL(nccl().AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
   return LLZ_OK;
 }
 
@@ -34,7 +87,7 @@ int comm_allreduce_partials(llz_ctx_t ctx, double* d, int* count) {
   if (ctx->nranks == 1) return LLZ_OK;
   // fold this rank's per-CTA partials into d[0] (fixed order), then sum over the group
   LLZ_TRY(launch_sum_partials(ctx, d, *count, 1, d, nullptr));
-  LLZ_NCCL(ncclAllReduce(d, d, 1, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
+  LLZ_NCCL(nccl().AllReduce(d, d, 1, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
   *count = 1;
   return LLZ_OK;
 }
@@ -47,7 +100,7 @@ int comm_allgather_bytes(llz_ctx_t ctx, const void* send, void* recv, size_t byt
     }
     return LLZ_OK;
   }
-  LLZ_NCCL(ncclAllGather(send, recv, bytes_per_rank, ncclChar, ctx->comm->nccl, ctx->stream));
+  LLZ_NCCL(nccl().AllGather(send, recv, bytes_per_rank, ncclChar, ctx->comm->nccl, ctx->stream));
   return LLZ_OK;
 }
 
@@ -56,13 +109,13 @@ int comm_allgather_bytes(llz_ctx_t ctx, const void* send, void* recv, size_t byt
 int comm_exchange(llz_ctx_t ctx, const char* send_base, const size_t* send_off, const size_t* send_bytes,
                   char* recv_base, const size_t* recv_off, const size_t* recv_bytes) {
   if (ctx->nranks == 1) return LLZ_OK;
-  LLZ_NCCL(ncclGroupStart());
+  LLZ_NCCL(nccl().GroupStart());
   for (int p = 0; p < ctx->nranks; ++p) {
     if (p == ctx->rank) continue;
-    if (send_bytes[p]) LLZ_NCCL(ncclSend(send_base + send_off[p], send_bytes[p], ncclChar, p, ctx->comm->nccl, ctx->stream));
-    if (recv_bytes[p]) LLZ_NCCL(ncclRecv(recv_base + recv_off[p], recv_bytes[p], ncclChar, p, ctx->comm->nccl, ctx->stream));
+    if (send_bytes[p]) LLZ_NCCL(nccl().Send(send_base + send_off[p], send_bytes[p], ncclChar, p, ctx->comm->nccl, ctx->stream));
+    if (recv_bytes[p]) LLZ_NCCL(nccl().Recv(recv_base + recv_off[p], recv_bytes[p], ncclChar, p, ctx->comm->nccl, ctx->stream));
   }
-  LLZ_NCCL(ncclGroupEnd());
+  LLZ_NCCL(nccl().GroupEnd());
   return LLZ_OK;
 }
 
@@ -89,9 +142,116 @@ int comm_allgather_host(llz_ctx_t ctx, const void* send, void* recv, size_t byte
   return s;
 }
 
+// ---- peer-memory channels ------------------------------------------------------------------------------------
+constexpr int kCoefPayload = 32768;  // doubles per slot of the coefficient channel (columns x NC + 1 must fit)
+constexpr int kScalarPayload = 8;
+
+static size_t channel_bytes(int G, int payload) { return ((size_t)2 * G * payload + (size_t)2 * G) * sizeof(double); }
+
+// Collective over the group (called from llz_ctx_join): every rank allocates its inbox, exports it with CUDA IPC,
+// all-gathers the handles over NCCL and maps every peer's inbox.  Any failure on any rank (IPC not permitted, no
+// peer access) leaves the whole group on the NCCL path — decided together, so the ranks never disagree.
+static int p2p_setup(llz_ctx_t ctx) {
+  Comm* c = ctx->comm;
+  const int G = ctx->nranks;
+  const char* env = getenv("LLZ_P2P");
+  int want = !(env && env[0] == '0');
+  const size_t bytes = channel_bytes(G, kScalarPayload) * 2 + channel_bytes(G, kCoefPayload) + 256;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  int ok = want;
+  if (ok && cudaMalloc(&c->p2p_local, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaMemset(c->p2p_local, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, c->p2p_local) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  struct Rec {
+    cudaIpcMemHandle_t h;
+    int ok;
+    int pad;
+  };
+  Rec rec;
+  memset(&rec, 0, sizeof(rec));
+  rec.h = mine;
+  rec.ok = ok;
+  std::vector<Rec> all((size_t)G);
+  LLZ_TRY(comm_allgather_host(ctx, &rec, all.data(), sizeof(Rec)));
+  for (int r = 0; r < G; ++r) ok = ok && all[(size_t)r].ok;
+  if (ok) {
+    for (int r = 0; r < G && ok; ++r) {
+      if (r == ctx->rank) {
+        c->p2p_peer[r] = c->p2p_local;
+        continue;
+      }
+      if (cudaIpcOpenMemHandle(&c->p2p_peer[r], all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        c->p2p_peer[r] = nullptr;
+        ok = 0;
+      }
+    }
+  }
+  // second round: did every rank map every peer?
+  int mapped = ok;
+  std::vector<int> mapped_all((size_t)G);
+  LLZ_TRY(comm_allgather_host(ctx, &mapped, mapped_all.data(), sizeof(int)));
+  for (int r = 0; r < G; ++r) ok = ok && mapped_all[(size_t)r];
+  if (!ok) {
+    for (int r = 0; r < G; ++r)
+      if (r != ctx->rank && c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+    if (c->p2p_local) cudaFree(c->p2p_local);
+    c->p2p_local = nullptr;
+    memset(c->p2p_peer, 0, sizeof(c->p2p_peer));
+    cudaGetLastError();
+    return LLZ_OK;  // NCCL path
+  }
+  const int payload[3] = {kScalarPayload, kScalarPayload, kCoefPayload};
+  size_t off = 256;  // first 256 bytes: status word (+0) and the last-CTA ticket (+64)
+  for (int k = 0; k < 3; ++k) {
+    PeerChannel& ch = c->ch[k];
+    ch.G = G;
+    ch.rank = ctx->rank;
+    ch.payload = payload[k];
+    ch.status = reinterpret_cast<unsigned long long*>(c->p2p_local);
+    for (int r = 0; r < G; ++r) ch.inbox[r] = reinterpret_cast<double*>(static_cast<char*>(c->p2p_peer[r]) + off);
+    off += channel_bytes(G, payload[k]);
+  }
+  c->ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(c->p2p_local) + 64);
+  return LLZ_OK;
+}
+
+bool comm_p2p(llz_ctx_t ctx) { return ctx->nranks > 1 && ctx->comm && ctx->comm->ch[0].G > 0; }
+int comm_coef_capacity(llz_ctx_t ctx) { return comm_p2p(ctx) ? kCoefPayload : 0; }
+unsigned int* comm_ticket(llz_ctx_t ctx) { return comm_p2p(ctx) ? ctx->comm->ticket : nullptr; }
+
+// The channel and the sequence number of its NEXT message (every rank calls this in the same order).
+PeerChannel comm_next_message(llz_ctx_t ctx, int which, unsigned long long* seq) {
+  Comm* c = ctx->comm;
+  *seq = ++c->seq[which];
+  return c->ch[which];
+}
+
+// Non-zero when a kernel gave up waiting for a peer (the peer process died or diverged).
+int comm_check_peers(llz_ctx_t ctx) {
+  if (!comm_p2p(ctx)) return LLZ_OK;
+  unsigned long long st = 0;
+  if (cudaMemcpy(&st, ctx->comm->p2p_local, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(LLZ_ERR_CUDA, "peer status read failed");
+  if (st) return fail(LLZ_ERR_COMM, "a kernel timed out waiting for message %llu of a peer GPU", st & ~(1ull << 63));
+  return LLZ_OK;
+}
+
 void comm_destroy(llz_ctx_t ctx) {
+  if (ctx->comm && ctx->comm->p2p_local) {
+    Comm* c = ctx->comm;
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+    // every rank must have unmapped this rank's inbox before it is freed: one blocking collective
+    double* d = ctx->d_result;
+    if (d && nccl().AllReduce(d, d, 1, ncclDouble, ncclSum, c->nccl, ctx->stream) == ncclSuccess) cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->p2p_local);
+    c->p2p_local = nullptr;
+    cudaGetLastError();
+  }
   if (ctx->comm) {
-    if (ctx->comm->nccl) ncclCommDestroy(ctx->comm->nccl);
+    if (ctx->comm->nccl) nccl().CommDestroy(ctx->comm->nccl);
     delete ctx->comm;
     ctx->comm = nullptr;
   }
@@ -103,11 +263,18 @@ using namespace llz;
 
 extern "C" {
 
+int llz_ctx_peer_channels(llz_ctx_t ctx, int* enabled) {
+  if (!ctx || !enabled) return fail(LLZ_ERR_INVALID, "null argument");
+  *enabled = comm_p2p(ctx) ? 1 : 0;
+  return LLZ_OK;
+}
+
 int llz_comm_unique_id(void* id128) {
   if (!id128) return fail(LLZ_ERR_INVALID, "null id buffer");
+  if (!nccl().ok) return fail(LLZ_ERR_COMM, "NCCL unavailable: %s", nccl().why);
   static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId larger than the 128-byte blob of the ABI");
   ncclUniqueId id;
-  LLZ_NCCL(ncclGetUniqueId(&id));
+  LLZ_NCCL(nccl().GetUniqueId(&id));
   memset(id128, 0, 128);
   memcpy(id128, &id, sizeof(id));
   return LLZ_OK;
@@ -118,19 +285,21 @@ int llz_ctx_join(llz_ctx_t ctx, int rank, int nranks, const void* id128) {
   if (ctx->comm) return fail(LLZ_ERR_INVALID, "ctx_join: context already joined");
   if (nranks == 1) return LLZ_OK;
   if (!id128) return fail(LLZ_ERR_INVALID, "ctx_join: null id");
+  if (nranks > kMaxRanks) return fail(LLZ_ERR_UNSUPPORTED, "ctx_join: at most %d ranks (one box)", kMaxRanks);
+  if (!nccl().ok) return fail(LLZ_ERR_COMM, "NCCL unavailable: %s", nccl().why);
   LLZ_CUDA(cudaSetDevice(ctx->device));
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   Comm* c = new Comm();
-  ncclResult_t r = ncclCommInitRank(&c->nccl, nranks, id, rank);
+  ncclResult_t r = nccl().CommInitRank(&c->nccl, nranks, id, rank);
   if (r != ncclSuccess) {
     delete c;
-    return fail(LLZ_ERR_COMM, "ncclCommInitRank: %s", ncclGetErrorString(r));
+    return fail(LLZ_ERR_COMM, "ncclCommInitRank: %s", nccl().GetErrorString(r));
   }
   ctx->comm = c;
   ctx->rank = rank;
   ctx->nranks = nranks;
-  return LLZ_OK;
+  return p2p_setup(ctx);
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // llz_ctx.cu — contexts, error reporting, device vectors and the stand-alone util:: vector operations.
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 
 #include "llz_launch.hpp"
@@ -25,6 +26,15 @@ int fail(int status, const char* fmt, ...) {
 }
 
 cudaError_t dev_malloc(llz_ctx_t ctx, void** p, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+  auto it = ctx->vec_pool.find(bytes);
+  if (it != ctx->vec_pool.end()) {
+    *p = it->second;
+    ctx->vec_pool.erase(it);
+    ctx->vec_pool_bytes -= bytes;
+    ctx->dev_sizes[*p] = bytes;
+    return cudaSuccess;
+  }
   cudaError_t e = cudaMalloc(p, bytes);
   if (e == cudaErrorMemoryAllocation && (ctx->cached_krylov || !ctx->vec_pool.empty())) {
     cudaGetLastError();
@@ -32,7 +42,21 @@ cudaError_t dev_malloc(llz_ctx_t ctx, void** p, size_t bytes) {
     ctx_trim(ctx);
     e = cudaMalloc(p, bytes);
   }
+  if (e == cudaSuccess) ctx->dev_sizes[*p] = bytes;
   return e;
+}
+
+void dev_free(llz_ctx_t ctx, void* p) {
+  if (!p) return;
+  auto it = ctx->dev_sizes.find(p);
+  if (it == ctx->dev_sizes.end()) {  // not ours: plain free
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+    return;
+  }
+  const size_t bytes = it->second;
+  ctx->dev_sizes.erase(it);
+  ctx_free(ctx, p, bytes);
 }
 
 int ctx_alloc(llz_ctx_t ctx, size_t bytes, void** out) {

@@ -106,6 +106,22 @@ __device__ __forceinline__ double2 mul(double2 c, double2 v) {
   return make_double2(c.x * v.x - c.y * v.y, c.x * v.y + c.y * v.x);
 }
 
+// Product and sum with one rounding each and NO fused contraction, whatever -fmad says: the arithmetic of a plain
+// `out[i] += a * x[j]` loop compiled for a CPU without FMA contraction (the reference's sample-style mv_mul), so the
+// SpMV kernels that use them reproduce the CPU's y bit for bit.
+__device__ __forceinline__ float mul_rn(float c, float v) { return __fmul_rn(c, v); }
+__device__ __forceinline__ double mul_rn(double c, double v) { return __dmul_rn(c, v); }
+__device__ __forceinline__ float2 mul_rn(float2 c, float2 v) {
+  return make_float2(__fsub_rn(__fmul_rn(c.x, v.x), __fmul_rn(c.y, v.y)), __fadd_rn(__fmul_rn(c.x, v.y), __fmul_rn(c.y, v.x)));
+}
+__device__ __forceinline__ double2 mul_rn(double2 c, double2 v) {
+  return make_double2(__dsub_rn(__dmul_rn(c.x, v.x), __dmul_rn(c.y, v.y)), __dadd_rn(__dmul_rn(c.x, v.y), __dmul_rn(c.y, v.x)));
+}
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float2 add_rn(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 add_rn(double2 a, double2 b) { return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y)); }
+
 __device__ __forceinline__ double abs2(float v) { return (double)v * (double)v; }
 __device__ __forceinline__ double abs2(double v) { return v * v; }
 __device__ __forceinline__ double abs2(float2 v) { return (double)v.x * v.x + (double)v.y * v.y; }

@@ -74,6 +74,7 @@ struct llz_ctx_s {
   // ctx and reused across runs).  Everything runs on ONE stream, so a buffer handed back can be reused by later
   // stream-ordered work without a synchronisation.
   std::multimap<size_t, void*> vec_pool;  // free device buffers by size
+  std::map<void*, size_t> dev_sizes;      // live dev_malloc allocations
   size_t vec_pool_bytes = 0;
   size_t vec_pool_limit = 0;              // set at creation (a quarter of the device memory)
   llz_krylov_t cached_krylov = nullptr;   // last destroyed Krylov workspace, revived by a matching llz_krylov_create
@@ -125,11 +126,21 @@ int comm_allreduce_sum(llz_ctx_t ctx, double* d, int count);
 // (d[0], *count = 1).
 int comm_allreduce_partials(llz_ctx_t ctx, double* d, int* count);
 void comm_destroy(llz_ctx_t ctx);
+// Peer-memory channels (llz_peer.cuh) set up by llz_ctx_join: 0 = alpha, 1 = beta^2, 2 = projection coefficients
+struct PeerChannel;
+bool comm_p2p(llz_ctx_t ctx);
+int comm_coef_capacity(llz_ctx_t ctx);
+unsigned int* comm_ticket(llz_ctx_t ctx);
+int comm_check_peers(llz_ctx_t ctx);
 // Pooled device allocations of a context (llz_ctx.cu)
 int ctx_alloc(llz_ctx_t ctx, size_t bytes, void** out);
 void ctx_free(llz_ctx_t ctx, void* p, size_t bytes);
-// cudaMalloc that gives the context's cached memory back to the driver and retries once when the device is full
+// Pooled device allocation for operator arrays: served from the context's free list when a buffer of the same
+// (256-byte rounded) size is there, else cudaMalloc — which gives the context's cached memory back to the driver and
+// retries once when the device is full.  dev_free returns the buffer to the free list (safe without a synchronisation
+// because every kernel and copy of a context is ordered on its one stream).
 cudaError_t dev_malloc(llz_ctx_t ctx, void** p, size_t bytes);
+void dev_free(llz_ctx_t ctx, void* p);
 template <class P> inline cudaError_t dev_malloc(llz_ctx_t ctx, P** p, size_t bytes) { return dev_malloc(ctx, (void**)p, bytes); }
 void ctx_trim(llz_ctx_t ctx);            // release every cached buffer (vector pool + cached Krylov workspace)
 void krylov_destroy_now(llz_krylov_t k); // really free a workspace (llz_krylov.cu)

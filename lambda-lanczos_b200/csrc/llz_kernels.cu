@@ -39,6 +39,7 @@ struct ProjectArgs {
   const void* u1;  // V[:, nv-1]
   const void* u2;  // V[:, nv-2]
   double* ph;
+  PeerMsg alpha_msg;
 };
 
 template <class T> __device__ __forceinline__ const T* column_ptr(const void* V, int64_t ld, const void* const* Q, int nq, int j) {
@@ -143,7 +144,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
 
   R alpha = 0, beta = 0;
   if (a.fold >= 1) {
-    const double al = block_sum_partials(a.pa, a.npa, scratch);
+    double al;
+    if (a.alpha_msg.ch.G > 0) {  // row-sharded: every rank delivered its part of <u, Au> to this GPU's inbox
+      peer_wait(a.alpha_msg.ch, a.alpha_msg.seq);
+      al = peer_sum(a.alpha_msg.ch, a.alpha_msg.seq, 0);
+    } else {
+      al = block_sum_partials(a.pa, a.npa, scratch);
+    }
     alpha = (R)al;
     if (blockIdx.x == 0 && tid == 0 && a.alpha_out) *a.alpha_out = al;
     if (a.fold >= 2) beta = (R)(*a.beta_prev);
@@ -179,18 +186,65 @@ struct ReduceArgs {
   double* wnorm2;  // receives sum of the extra ||w'||^2 slot (may be null)
   int width;  // ncols*NC of the chunk; each CTA row of ph holds width + 1 doubles
   double* coef;  // already offset to the chunk
+  // row-sharded with peer channels: deliver the sums to every rank's inbox instead
+  PeerMsg msg;
+  int slot_base;    // payload index of the chunk's first value
+  int wnorm_index;  // payload index of ||w'||^2, or -1
+  int publish;      // announce the message (last chunk of the pass)
+  unsigned int* ticket;
 };
 
-__global__ void __launch_bounds__(128) k_reduce(ReduceArgs a) {
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i > a.width) return;
+// 32 values per CTA; the 8 warps each add every 8th per-CTA partial (coalesced 256-byte rows), then the 8 partial sums
+// are added in a fixed order.  Row-sharded: the result goes straight into every peer's inbox over NVLink and the last
+// CTA to finish announces the message — no collective call between the projection and the update.
+__global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
+  __shared__ double part[kWarps][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int c = 0; c < a.grid; ++c) s += a.ph[(size_t)c * (a.width + 1) + i];
-  if (i == a.width) {
-    if (a.wnorm2) *a.wnorm2 = s;
-    return;
+  if (i <= a.width)
+    for (int c = ty; c < a.grid; c += kWarps) s += a.ph[(size_t)c * (a.width + 1) + i];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i <= a.width) {
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < kWarps; ++y) t += part[y][tx];
+    if (a.msg.ch.G > 0) {
+      const int idx = (i == a.width) ? a.wnorm_index : a.slot_base + i;
+      if (idx >= 0)
+        for (int p = 0; p < a.msg.ch.G; ++p) peer_slot(a.msg.ch, p, a.msg.seq, a.msg.ch.rank)[idx] = t;
+    } else if (i == a.width) {
+      if (a.wnorm2) *a.wnorm2 = t;
+    } else {
+      a.coef[i] = t;
+    }
   }
-  a.coef[i] = s;
+  if (a.msg.ch.G > 0 && a.publish) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(a.ticket, 1u);
+      if (t == gridDim.x - 1) {  // every CTA's stores are visible system-wide: announce
+        *a.ticket = 0;
+        __threadfence_system();
+        for (int p = 0; p < a.msg.ch.G; ++p) peer_announce(a.msg.ch, p, a.msg.seq);
+      }
+    }
+  }
+}
+
+// One CTA: group-wide delivery of a scalar that exists as per-CTA partials (alpha after the operator, ||u||^2 after the
+// update).  Thread p stores to rank p, fences and announces.
+__global__ void __launch_bounds__(kThreads) k_push_scalar(const double* __restrict__ partials, int count, PeerMsg msg) {
+  __shared__ double scratch[kWarps];
+  const double v = block_sum_partials(partials, count, scratch);
+  const int p = threadIdx.x;
+  if (p < msg.ch.G) {
+    peer_slot(msg.ch, p, msg.seq, msg.ch.rank)[0] = v;
+    __threadfence_system();
+    peer_announce(msg.ch, p, msg.seq);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -215,6 +269,7 @@ struct UpdateArgs {
   const void* u1;           // basis columns k-1 and k-2; their projection coefficients sit at coef[cu1], coef[cu2]
   const void* u2;
   int cu1, cu2;
+  PeerMsg coef_msg;  // row-sharded: coefficients = sum over ranks of this message (element col*NC + c)
 };
 
 template <class T, int VPT, bool FULL>
@@ -310,22 +365,28 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
   T* cs = reinterpret_cast<T*>(smem_u);
   __shared__ double scratch[kWarps];
   const int tid = threadIdx.x;
-  for (int i = tid; i < a.ncols; i += kThreads) {
-    const double* c = a.coef + (size_t)(a.col0 + i) * NC;
-    cs[i] = from_double<T>(c[0], NC == 2 ? c[NC - 1] : 0.0);
-  }
+  const bool peer = a.coef_msg.ch.G > 0;
+  if (peer) peer_wait(a.coef_msg.ch, a.coef_msg.seq);
+  auto coef_at = [&](int col) -> T {
+    if (peer) {
+      const double re = peer_sum(a.coef_msg.ch, a.coef_msg.seq, col * NC);
+      const double im = NC == 2 ? peer_sum(a.coef_msg.ch, a.coef_msg.seq, col * NC + 1) : 0.0;
+      return from_double<T>(re, im);
+    }
+    const double* c = a.coef + (size_t)col * NC;
+    return from_double<T>(c[0], NC == 2 ? c[NC - 1] : 0.0);
+  };
+  for (int i = tid; i < a.ncols; i += kThreads) cs[i] = coef_at(a.col0 + i);
   __syncthreads();
   using R = typename Num<T>::R;
   R alpha = 0, beta = 0;
   T h1 = zero_of(T()), h2 = zero_of(T());
   if (a.fold >= 1) {
     alpha = (R)(*a.alpha);
-    const double* c1 = a.coef + (size_t)a.cu1 * NC;
-    h1 = from_double<T>(c1[0], NC == 2 ? c1[NC - 1] : 0.0);
+    h1 = coef_at(a.cu1);
     if (a.fold >= 2) {
       beta = (R)(*a.beta_prev);
-      const double* c2 = a.coef + (size_t)a.cu2 * NC;
-      h2 = from_double<T>(c2[0], NC == 2 ? c2[NC - 1] : 0.0);
+      h2 = coef_at(a.cu2);
     }
   }
   constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
@@ -356,13 +417,24 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(S
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
   const int tid = threadIdx.x;
-  const double beta2 = block_sum_partials(a.pb, a.npb, scratch);
+  double beta2;
+  if (a.sink.beta_msg.ch.G > 0) {
+    peer_wait(a.sink.beta_msg.ch, a.sink.beta_msg.seq);
+    beta2 = peer_sum(a.sink.beta_msg.ch, a.sink.beta_msg.seq, 0);
+  } else {
+    beta2 = block_sum_partials(a.pb, a.npb, scratch);
+  }
   const double beta = sqrt(beta2);
   if (blockIdx.x == 0 && tid == 0) {
     if (a.sink.beta_out) *a.sink.beta_out = beta;
     if (a.sink.h_beta) *a.sink.h_beta = beta;
     if (a.sink.h_alpha && a.sink.alpha_in) *a.sink.h_alpha = *a.sink.alpha_in;
-    if (a.sink.h_wnorm) *a.sink.h_wnorm = a.sink.wnorm2_in ? sqrt(*a.sink.wnorm2_in) : beta;
+    if (a.sink.h_wnorm) {
+      double wn = beta;
+      if (a.sink.wnorm_msg.ch.G > 0) wn = sqrt(peer_sum(a.sink.wnorm_msg.ch, a.sink.wnorm_msg.seq, a.sink.wnorm_index));
+      else if (a.sink.wnorm2_in) wn = sqrt(*a.sink.wnorm2_in);
+      *a.sink.h_wnorm = wn;
+    }
     if (a.sink.h_flag) {
       __threadfence_system();
       *reinterpret_cast<volatile long long*>(a.sink.h_flag) = a.sink.flag_value;
@@ -397,6 +469,7 @@ struct RecurrenceArgs {
   const double* beta_prev;
   double* alpha_out;
   double* pb;
+  PeerMsg alpha_msg;
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
@@ -406,7 +479,13 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(R
   const int tid = threadIdx.x;
   R alpha = 0, beta = 0;
   if (a.fold >= 1) {
-    const double al = block_sum_partials(a.pa, a.npa, scratch);
+    double al;
+    if (a.alpha_msg.ch.G > 0) {
+      peer_wait(a.alpha_msg.ch, a.alpha_msg.seq);
+      al = peer_sum(a.alpha_msg.ch, a.alpha_msg.seq, 0);
+    } else {
+      al = block_sum_partials(a.pa, a.npa, scratch);
+    }
     alpha = (R)al;
     if (blockIdx.x == 0 && tid == 0 && a.alpha_out) *a.alpha_out = al;
     if (a.fold >= 2) beta = (R)(*a.beta_prev);
@@ -715,6 +794,7 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
   a.npa = fold.n_partials;
   a.beta_prev = fold.beta_prev;
   a.alpha_out = fold.alpha_out;
+  a.alpha_msg = fold.alpha_msg;
   a.ph = ph;
   const size_t es = dtype_size(dtype);
   a.u1 = cs.nv >= 1 ? (const char*)cs.V + (size_t)(cs.nv - 1) * cs.ld * es : nullptr;
@@ -728,7 +808,8 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
   return LLZ_OK;
 }
 
-int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2) {
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2,
+                  const PeerMsg& msg, int wnorm_index, int publish) {
   const int nc = dtype_nc(dtype);
   ReduceArgs a;
   a.ph = ph;
@@ -736,8 +817,18 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
   a.wnorm2 = wnorm2;
   a.width = ncols * nc;
   a.coef = coef + (size_t)col0 * nc;
-  k_reduce<<<(a.width + 1 + 127) / 128, 128, 0, ctx->stream>>>(a);
+  a.msg = msg;
+  a.slot_base = col0 * nc;
+  a.wnorm_index = wnorm_index;
+  a.publish = publish;
+  a.ticket = comm_ticket(ctx);
+  k_reduce<<<(a.width + 1 + 31) / 32, kThreads, 0, ctx->stream>>>(a);
   return check_launch(ctx, "k_reduce");
+}
+
+int launch_push_scalar(llz_ctx_t ctx, const double* partials, int count, const PeerMsg& msg) {
+  k_push_scalar<<<1, kThreads, 0, ctx->stream>>>(partials, count, msg);
+  return check_launch(ctx, "k_push_scalar");
 }
 
 template <class T, int VPT>
@@ -752,7 +843,8 @@ static int update_impl(llz_ctx_t ctx, const UpdateArgs& a, int* grid_out) {
 }
 
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
-                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out) {
+                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
+                  const PeerMsg& coef_msg) {
   if (ncols < 0 || ncols > max_update_cols(dtype)) return fail(LLZ_ERR_INVALID, "update: %d columns per launch", ncols);
   UpdateArgs a;
   a.V = cs.V;
@@ -765,6 +857,7 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
   a.out = out;
   a.n = n;
   a.coef = coef;
+  a.coef_msg = coef_msg;
   a.pb = norm_partials;
   a.fold = fold.mode;
   a.alpha = fold.alpha_out;
@@ -812,6 +905,7 @@ int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, c
   a.npa = fold.n_partials;
   a.beta_prev = fold.beta_prev;
   a.alpha_out = fold.alpha_out;
+  a.alpha_msg = fold.alpha_msg;
   a.pb = norm_partials;
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;

@@ -157,15 +157,43 @@ int ensure_ph(llz_krylov_t kry, size_t doubles) {
 
 // One classical Gram-Schmidt pass of `w` against cs: project -> reduce -> update (in place).  With an empty column
 // set only the update kernel runs (it then just produces the norm partials of w).
-int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, bool want_norm, int* norm_grid) {
+// Group-wide scalar held as per-CTA partials (alpha after the operator, ||u||^2 after the update): with peer channels
+// one tiny kernel delivers this rank's sum to every inbox and the consumer adds the G parts in its prologue; otherwise
+// the partials are folded and all-reduced over NCCL (count becomes 1).  Single rank: nothing to do.
+int share_scalar(llz_ctx_t ctx, int channel, double* partials, int* count, PeerMsg* msg) {
+  *msg = PeerMsg();
+  if (ctx->nranks == 1) return LLZ_OK;
+  if (comm_p2p(ctx)) {
+    msg->ch = comm_next_message(ctx, channel, &msg->seq);
+    ProfScope ps(ctx, "exchange", 0.0);
+    return launch_push_scalar(ctx, partials, *count, *msg);
+  }
+  ProfScope ps(ctx, "exchange", 0.0);
+  return comm_allreduce_partials(ctx, partials, count);
+}
+
+// One classical Gram-Schmidt pass of `w` against cs: project -> reduce -> update (in place).  With an empty column
+// set only the update kernel runs (it then just produces the norm partials of w).  `wnorm` tells the caller where
+// ||w'||^2 of this pass can be read (peer message element or kry->d_misc[1]).
+int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, bool want_norm, int* norm_grid,
+             PeerMsg* wnorm_msg = nullptr, int* wnorm_index = nullptr) {
   llz_ctx_t ctx = kry->ctx;
   const int nc = dtype_nc(kry->dtype);
   const int total = cs.ncols();
   const int max_grid = std::min(kMaxGrid, ctx->num_sms * 2);
+  PeerMsg coef_msg;  // row-sharded with peer channels: the coefficients travel as one message
+  if (wnorm_msg) *wnorm_msg = PeerMsg();
   if (total > 0) {
+    const bool peer = comm_p2p(ctx) && total * nc + 1 <= comm_coef_capacity(ctx);
+    if (peer) {
+      coef_msg.ch = comm_next_message(ctx, kChanCoef, &coef_msg.seq);
+      if (wnorm_msg) *wnorm_msg = coef_msg;
+      if (wnorm_index) *wnorm_index = total * nc;
+    }
     const int pchunk = max_project_cols(kry->dtype);
     for (int c0 = 0; c0 < total; c0 += pchunk) {
       const int cols = std::min(pchunk, total - c0);
+      const bool last = c0 + cols >= total;
       LLZ_TRY(ensure_ph(kry, (size_t)max_grid * ((size_t)cols * nc + 1)));
       int grid = 0;
       {
@@ -174,12 +202,15 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
       }
       {
         ProfScope ps(ctx, "reduce", 0.0);
-        LLZ_TRY(launch_reduce(ctx, kry->dtype, kry->d_ph, grid, c0, cols, kry->d_coef,
-                              (c0 + cols >= total) ? kry->d_misc + 1 : nullptr));
+        LLZ_TRY(launch_reduce(ctx, kry->dtype, kry->d_ph, grid, c0, cols, kry->d_coef, last ? kry->d_misc + 1 : nullptr, coef_msg,
+                              last ? total * nc : -1, last ? 1 : 0));
       }
     }
-    LLZ_TRY(comm_allreduce_sum(ctx, kry->d_coef, total * nc));
-    LLZ_TRY(comm_allreduce_sum(ctx, kry->d_misc + 1, 1));
+    if (!peer && ctx->nranks > 1) {
+      ProfScope ps(ctx, "exchange", 0.0);
+      LLZ_TRY(comm_allreduce_sum(ctx, kry->d_coef, total * nc));
+      LLZ_TRY(comm_allreduce_sum(ctx, kry->d_misc + 1, 1));
+    }
   }
   // update: the fold.mode trailing basis columns are consumed by the kernel's recurrence prologue (first chunk)
   const int generic = total - fold.mode;
@@ -191,7 +222,7 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
     Fold f = (c0 == 0) ? fold : Fold();
     ProfScope ps(ctx, "update", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + f.mode + 2));
     LLZ_TRY(launch_update(ctx, kry->dtype, cs, c0, cols, w, w, kry->n, kry->d_coef, f,
-                          (last && want_norm) ? kry->d_pb : nullptr, norm_grid));
+                          (last && want_norm) ? kry->d_pb : nullptr, norm_grid, coef_msg));
     c0 += cols;
   } while (c0 < generic);
   return LLZ_OK;
@@ -405,8 +436,8 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   // the start vector may lie almost inside span(locked): orthogonalise twice ("twice is enough")
   if (kry->nq > 0) LLZ_TRY(cgs_pass(kry, cs, u0, nofold, false, &grid));
   LLZ_TRY(cgs_pass(kry, cs, u0, nofold, true, &grid));
-  LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
   ScalarSink sink;
+  LLZ_TRY(share_scalar(ctx, kChanBeta, kry->d_pb, &grid, &sink.beta_msg));
   sink.beta_out = kry->d_misc;
   sink.h_beta = kry->h_misc;
   {
@@ -414,6 +445,7 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
     LLZ_TRY(launch_scale_by_norm(ctx, kry->dtype, u0, kry->n, kry->d_pb, grid, sink));
   }
   LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  LLZ_TRY(comm_check_peers(ctx));
   if (norm_out) *norm_out = kry->h_misc[0];
   return LLZ_OK;
 }
@@ -439,9 +471,8 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     ProfScope ps(ctx, "dot", (double)kry->n * (double)dtype_size(kry->dtype) * 2);
     LLZ_TRY(launch_redot(ctx, kry->dtype, x, y, kry->n, kry->d_pa, &npa));
   }
-  LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pa, &npa));
-
   Fold fold;
+  LLZ_TRY(share_scalar(ctx, kChanAlpha, kry->d_pa, &npa, &fold.alpha_msg));
   fold.mode = (k == 1) ? 1 : 2;
   fold.alpha_partials = kry->d_pa;
   fold.n_partials = npa;
@@ -449,6 +480,7 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
   fold.alpha_out = kry->d_alpha + (k - 1);
 
   int grid = 0;
+  ScalarSink sink;
   if (orth == LLZ_ORTH_RECURRENCE) {
     ProfScope ps(ctx, "recurrence", (double)kry->n * (double)dtype_size(kry->dtype) * (2 + fold.mode));
     LLZ_TRY(launch_recurrence(ctx, kry->dtype, y, kry->col(k - 1), k >= 2 ? kry->col(k - 2) : nullptr, y, kry->n, fold,
@@ -460,14 +492,13 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     cs.nv = (int)k;
     cs.Q = (const void* const*)kry->d_qptrs;
     cs.nq = kry->nq;
-    LLZ_TRY(cgs_pass(kry, cs, y, fold, true, &grid));
+    LLZ_TRY(cgs_pass(kry, cs, y, fold, true, &grid, &sink.wnorm_msg, &sink.wnorm_index));
     if (orth == LLZ_ORTH_FULL_TWICE) {
       Fold nofold;
       LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
     }
   }
-  LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
-  ScalarSink sink;
+  LLZ_TRY(share_scalar(ctx, kChanBeta, kry->d_pb, &grid, &sink.beta_msg));
   sink.beta_out = kry->d_beta + (k - 1);
   sink.alpha_in = kry->d_alpha + (k - 1);
   sink.h_alpha = kry->h_alpha + (k - 1);
@@ -521,8 +552,8 @@ int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink) {
   Fold nofold;
   int grid = 0;
   LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
-  LLZ_TRY(comm_allreduce_partials(ctx, kry->d_pb, &grid));
   ScalarSink sink;
+  LLZ_TRY(share_scalar(ctx, kChanBeta, kry->d_pb, &grid, &sink.beta_msg));
   sink.beta_out = kry->d_misc;
   sink.h_beta = kry->h_misc;
   {
@@ -590,6 +621,10 @@ int llz_krylov_combine(llz_krylov_t kry, int64_t m, int64_t nvec, const void* co
         LLZ_TRY(launch_scale_by_norm(ctx, kry->dtype, outs[r], kry->n, kry->d_pb + (size_t)r * kMaxGrid, g, none));
       }
     }
+  }
+  if (comm_p2p(ctx)) {  // end of a run: report a peer that stopped answering instead of returning garbage
+    LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    LLZ_TRY(comm_check_peers(ctx));
   }
   return LLZ_OK;
 }

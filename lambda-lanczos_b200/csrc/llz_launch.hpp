@@ -1,8 +1,20 @@
 // llz_launch.hpp — typed-erased launchers of the streaming kernels (llz_kernels.cu).  All launch on ctx->stream.
 #pragma once
 #include "llz_internal.hpp"
+#include "llz_peer.cuh"
 
 namespace llz {
+
+// The channel and the sequence number of its NEXT message (llz_comm.cu; every rank calls this in the same order).
+PeerChannel comm_next_message(llz_ctx_t ctx, int which, unsigned long long* seq);
+enum { kChanAlpha = 0, kChanBeta = 1, kChanCoef = 2 };
+
+// A group-wide scalar or coefficient vector delivered through a peer-memory channel: message `seq` of `ch`.
+// ch.G == 0 means "not used": the consumer reads this rank's own device memory instead.
+struct PeerMsg {
+  PeerChannel ch;
+  unsigned long long seq = 0;
+};
 
 // The set of orthonormal columns a vector is projected on: `nq` separately allocated vectors (device pointer table)
 // followed by `nv` contiguous columns of the Krylov basis.  Column index space: [0,nq) = Q, [nq,nq+nv) = V.
@@ -23,6 +35,7 @@ struct Fold {
   int n_partials = 0;
   const double* beta_prev = nullptr;    // device address of beta_{k-2}
   double* alpha_out = nullptr;          // device address receiving alpha_{k-1}
+  PeerMsg alpha_msg;                    // row-sharded: alpha = sum over ranks of this message instead of the partials
 };
 
 // Where scale_by_norm publishes the iteration's scalars.
@@ -35,6 +48,9 @@ struct ScalarSink {
   double* h_wnorm = nullptr;      // mapped pinned slot receiving ||w'||
   long long* h_flag = nullptr;    // mapped pinned: set to `flag_value` after the scalars are visible
   long long flag_value = 0;
+  PeerMsg beta_msg;               // row-sharded: ||u||^2 = sum over ranks of this message instead of the partials
+  PeerMsg wnorm_msg;              // row-sharded: ||w'||^2 = element wnorm_index of this (already awaited) message
+  int wnorm_index = 0;
 };
 
 int max_project_cols(int dtype);  // columns one projection launch can accumulate in shared memory
@@ -46,12 +62,19 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
                    const Fold& fold, double* ph, int* grid_out);
 // coef[(col0+j)*NC+c] = sum_cta ph[cta][j*NC+c]
 // ph rows hold ncols*NC + 1 doubles: the last one is the CTA's partial of ||w'||^2, summed into *wnorm2 if non-null.
-int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2);
+// Row-sharded with peer channels: `msg` (ch.G > 0) receives this rank's sums instead of coef/wnorm2 — element
+// (col0+j)*NC+c for the coefficients, element wnorm_index for ||w'||^2 (if >= 0) — in EVERY rank's inbox, and the
+// message is announced when `publish` is set (last chunk of a pass).
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2,
+                  const PeerMsg& msg = PeerMsg(), int wnorm_index = -1, int publish = 0);
+// One CTA: sums `count` per-CTA partials and delivers the result as element 0 of message `msg` to every rank.
+int launch_push_scalar(llz_ctx_t ctx, const double* partials, int count, const PeerMsg& msg);
 // out = w' - sum_j coef_j col_j over the chunk [col0, col0+ncols), where w' = w - alpha u_{k-1} - beta u_{k-2} per `fold`
 // (then the chunk must EXCLUDE those fold.mode trailing basis columns: the kernel applies their coefficients itself).
 // If norm_partials != null, per-CTA partials of ||out||^2.
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
-                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out);
+                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
+                  const PeerMsg& coef_msg = PeerMsg());
 // x *= 1/sqrt(sum partials); publishes beta (and alpha) per `sink`.  Leaves x untouched when the norm is not > 0.
 int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
                          const ScalarSink& sink);

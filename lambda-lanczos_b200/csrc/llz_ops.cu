@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(kThreads, 4)
     __syncthreads();
     const IDX base = rp[0];
     const int cnt = (int)(rp[nrows] - base);
-    for (int e = tid; e < cnt; e += kThreads) prod[e] = mul(vals[base + e], gather_x(x, halo, colidx[base + e], nloc));
+    for (int e = tid; e < cnt; e += kThreads) prod[e] = mul_rn(vals[base + e], gather_x(x, halo, colidx[base + e], nloc));
     __syncthreads();
     for (int r = tid; r < nrows; r += kThreads) {
       const int j1 = (int)(rp[r + 1] - base);
       T s = zero_of(T());
-      for (int j = (int)(rp[r] - base); j < j1; ++j) s = add_t(s, prod[j]);
+      for (int j = (int)(rp[r] - base); j < j1; ++j) s = add_rn(s, prod[j]);
       const T xi = x[row0 + r];
       const T yi = add_t(s, scale_real(xi, sigma));
       y[row0 + r] = yi;
@@ -181,47 +181,72 @@ __global__ void __launch_bounds__(kThreads) k_sell_fill(const IDX* __restrict__ 
   }
 }
 
+// Each warp walks TWO adjacent slices per step (64 rows: 2 x 5 x 384 B of matrix data in flight per warp on a 5-point
+// stencil) and fetches the slice pointers of its next step before it starts on the current one, so the three dependent
+// round trips (slice pointer -> column/value -> x gather) of consecutive steps overlap.
 template <class T>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
     k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
                     const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
                     T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa) {
   __shared__ double scratch[kWarps];
+  constexpr int U = 2;  // slices per warp step
   const int lane = threadIdx.x & 31;
   double dot = 0.0;
-  for (int64_t s = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s < n_slices; s += (int64_t)gridDim.x * kWarps) {
-    const int64_t p0 = __ldg(slice_ptr + s);
-    const int w = (int)((__ldg(slice_ptr + s + 1) - p0) / kSellC);
-    const int32_t* __restrict__ cp = scol + p0 + lane;
-    const T* __restrict__ vp = sval + p0 + lane;
-    T sum = zero_of(T());
-    int j = 0;
-    for (; j + 4 <= w; j += 4) {
-      int32_t c[4];
-      T v[4], xv[4];
+  const int64_t stride = (int64_t)gridDim.x * kWarps * U;
+  int64_t s0 = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * U;
+  // lanes 0..U hold slice_ptr[s0 + lane] (clamped), refreshed one step ahead
+  auto fetch_ptr = [&](int64_t first) -> int64_t {
+    const int64_t i = first + lane;
+    return (lane <= U && first < n_slices) ? __ldg(slice_ptr + (i <= n_slices ? i : n_slices)) : 0;
+  };
+  int64_t sp = fetch_ptr(s0);
+  for (; s0 < n_slices; s0 += stride) {
+    int64_t p0[U];
+    int w[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        c[u] = __ldg(cp + (int64_t)(j + u) * kSellC);
-        v[u] = __ldg(vp + (int64_t)(j + u) * kSellC);
+    for (int u = 0; u < U; ++u) {
+      const int64_t a = __shfl_sync(0xffffffffu, sp, u), b = __shfl_sync(0xffffffffu, sp, u + 1);
+      p0[u] = a;
+      w[u] = (s0 + u < n_slices) ? (int)((b - a) / kSellC) : 0;
+    }
+    sp = fetch_ptr(s0 + stride);
+    T sum[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sum[u] = zero_of(T());
+    const int wmax = max(w[0], w[1]);
+    for (int j = 0; j < wmax; j += 4) {
+      int32_t c[U][4];
+      T v[U][4], xv[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool in = j + q < w[u];
+          const int64_t at = p0[u] + (int64_t)(j + q) * kSellC + lane;
+          c[u][q] = in ? __ldg(scol + at) : -1;
+          v[u][q] = in ? __ldg(sval + at) : zero_of(T());
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[u][q] = c[u][q] >= 0 ? gather_x(x, halo, c[u][q], nloc) : zero_of(T());
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c[u][q] >= 0) sum[u] = add_rn(sum[u], mul_rn(v[u][q], xv[u][q]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = (s0 + u) * kSellC + lane;
+      if (r < n) {
+        const int64_t out = perm ? perm[r] : r;
+        const T xi = x[out];
+        const T yi = add_t(sum[u], scale_real(xi, sigma));
+        y[out] = yi;
+        dot += re_conj_mul(xi, yi);
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) xv[u] = c[u] >= 0 ? gather_x(x, halo, c[u], nloc) : zero_of(T());
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c[u] >= 0) sum = add_t(sum, mul(v[u], xv[u]));
-    }
-    for (; j < w; ++j) {
-      const int32_t c = __ldg(cp + (int64_t)j * kSellC);
-      const T v = __ldg(vp + (int64_t)j * kSellC);
-      if (c >= 0) sum = add_t(sum, mul(v, gather_x(x, halo, c, nloc)));
-    }
-    const int64_t r = s * kSellC + lane;
-    if (r < n) {
-      const int64_t out = perm ? perm[r] : r;
-      const T xi = x[out];
-      const T yi = add_t(sum, scale_real(xi, sigma));
-      y[out] = yi;
-      dot += re_conj_mul(xi, yi);
     }
   }
   const double t = block_sum(dot, scratch);
@@ -254,16 +279,16 @@ template <class T> struct CsrOp : OpBase {
   int32_t* d_perm = nullptr;  // null when rows are not sorted (sigma = 1)
 
   ~CsrOp() override {
-    if (d_slice_ptr) cudaFree(d_slice_ptr);
-    if (d_scol) cudaFree(d_scol);
-    if (d_sval) cudaFree(d_sval);
-    if (d_perm) cudaFree(d_perm);
-    if (d_rowptr) cudaFree(d_rowptr);
-    if (d_colidx) cudaFree(d_colidx);
-    if (d_vals) cudaFree(d_vals);
-    if (d_halo) cudaFree(d_halo);
-    if (d_sendbuf) cudaFree(d_sendbuf);
-    if (d_send_idx) cudaFree(d_send_idx);
+    if (d_slice_ptr) dev_free(ctx, d_slice_ptr);
+    if (d_scol) dev_free(ctx, d_scol);
+    if (d_sval) dev_free(ctx, d_sval);
+    if (d_perm) dev_free(ctx, d_perm);
+    if (d_rowptr) dev_free(ctx, d_rowptr);
+    if (d_colidx) dev_free(ctx, d_colidx);
+    if (d_vals) dev_free(ctx, d_vals);
+    if (d_halo) dev_free(ctx, d_halo);
+    if (d_sendbuf) dev_free(ctx, d_sendbuf);
+    if (d_send_idx) dev_free(ctx, d_send_idx);
   }
   int32_t nloc32() const { return (int32_t)std::min<int64_t>(n_local, 0x7fffffff); }
 
@@ -327,7 +352,8 @@ template <class T> struct CsrOp : OpBase {
   }
 
   int launch_sell(const void* x, void* y, double sigma, double* pa, int* npa) {
-    int64_t g = std::min<int64_t>((n_slices + kWarps - 1) / kWarps, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
+    const int64_t per_cta = kWarps * 2;  // slices one CTA covers per step
+    int64_t g = std::min<int64_t>((n_slices + per_cta - 1) / per_cta, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
     k_sell_spmv_dot<T><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, d_halo, nloc32(), (T*)y,
                                                             n_local, n_slices, (typename Num<T>::R)sigma, pa);
@@ -379,7 +405,7 @@ template <class T> struct CsrOp : OpBase {
           total = sorted_total;
           sigma = 256;
         } else if (s == LLZ_OK) {
-          cudaFree(d_perm);
+          dev_free(ctx, d_perm);
           d_perm = nullptr;
           s = widths_for(nullptr, &total);
           sigma = 1;
@@ -394,8 +420,8 @@ template <class T> struct CsrOp : OpBase {
       if (s == LLZ_OK) s = widths_for(d_perm, &total);
     }
     if (s != LLZ_OK) {
-      cudaFree(d_len);
-      cudaFree(d_width);
+      dev_free(ctx, d_len);
+      dev_free(ctx, d_width);
       return s;
     }
     sell_sigma = sigma;
@@ -411,12 +437,12 @@ template <class T> struct CsrOp : OpBase {
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_len);
-    cudaFree(d_width);
+    dev_free(ctx, d_len);
+    dev_free(ctx, d_width);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "SELL conversion: %s", cudaGetErrorString(e));
-    cudaFree(d_rowptr);
-    cudaFree(d_colidx);
-    cudaFree(d_vals);
+    dev_free(ctx, d_rowptr);
+    dev_free(ctx, d_colidx);
+    dev_free(ctx, d_vals);
     d_rowptr = nullptr;
     d_colidx = nullptr;
     d_vals = nullptr;
@@ -500,7 +526,7 @@ static int plan_sharded_csr(CsrOp<T>* op, int64_t row0, const int64_t* rowptr, c
   LLZ_CUDA(cudaMemcpyAsync(d_req, req.data(), sizeof(int32_t) * req.size(), cudaMemcpyHostToDevice, ctx->stream));
   int s = comm_exchange(ctx, (const char*)d_req, req_off.data(), req_bytes.data(), (char*)op->d_send_idx, got_off.data(), got_bytes.data());
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_req);
+  dev_free(ctx, d_req);
   if (s != LLZ_OK) return s;
   if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "csr halo set-up: %s", cudaGetErrorString(e));
   return LLZ_OK;
@@ -574,7 +600,7 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
       for (int64_t i = 0; i <= n_rows; ++i) r32[(size_t)i] = (int32_t)rowptr[i];
       guard(dev_malloc(ctx, &op->d_rowptr, sizeof(int32_t) * (size_t)(n_rows + 1)), "rowptr alloc");
       if (s == LLZ_OK)
-        guard(cudaMemcpy(op->d_rowptr, r32.data(), sizeof(int32_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice), "rowptr copy");
+        guard(cudaMemcpyAsync(op->d_rowptr, r32.data(), sizeof(int32_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice, ctx->stream), "rowptr copy");
     } else {
       guard(dev_malloc(ctx, &op->d_rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)), "rowptr alloc");
       if (s == LLZ_OK) guard(cudaMemcpyAsync(op->d_rowptr, rowptr, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice, ctx->stream), "rowptr copy");
@@ -753,6 +779,7 @@ int llz_op_apply(llz_op_t op, llz_vec_t x, llz_vec_t y) {
     return fail(LLZ_ERR_INVALID, "op_apply: shape/dtype mismatch");
   int npa = 0;
   LLZ_TRY(o->prepare(x->d));
+  ProfScope ps(o->ctx, "spmv", (double)o->bytes + (double)o->n_local * (double)dtype_size(o->dtype) * 2);
   return o->apply_fused(x->d, y->d, 0.0, o->ctx->d_partials, &npa);
 }
 

@@ -46,48 +46,58 @@ __device__ __forceinline__ uint32_t gosper_next(uint32_t s) {
   return (t + 1) | (((~t & -~t) - 1) >> __ffs(s));
 }
 
-template <class T, int ITEMS>
+// states[r] = the r-th basis state of the local block (one unranking per 32 consecutive states, Gosper steps between).
+__global__ void __launch_bounds__(kThreads) k_xxz_states(uint32_t* __restrict__ states, int64_t n, int64_t row0, int L, int n_up) {
+  constexpr int CH = 32;
+  const int64_t nchunks = (n + CH - 1) / CH;
+  for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * kThreads) {
+    const int64_t first = c * CH;
+    uint32_t s = xxz_unrank(row0 + first, L, n_up);
+    const int cnt = (int)((n - first < CH) ? (n - first) : CH);
+    for (int i = 0; i < cnt; ++i) {
+      states[first + i] = s;
+      s = gosper_next(s);
+    }
+  }
+}
+
+// One thread per basis state, consecutive threads on consecutive states, and a loop over the BONDS that is uniform
+// across the warp: for a given bond the 32 lanes flip the same two bits of 32 consecutive states, so their targets are
+// (nearly) consecutive ranks — exactly consecutive whenever the lanes share the half of the bit string the bond does
+// not touch, because rank = lo[low half] + hi[high half] — and the x gathers coalesce into a few 128-byte lines
+// instead of 32 separate sectors.  The state itself comes from a 4-byte-per-row table (A_bytes = 4 n).
+template <class T>
 __global__ void __launch_bounds__(kThreads, 4)
-    k_xxz_apply(const T* __restrict__ x, T* __restrict__ y, XxzParams p, typename Num<T>::R sigma, double* pa) {
+    k_xxz_apply(const T* __restrict__ x, T* __restrict__ y, const uint32_t* __restrict__ states, XxzParams p,
+                typename Num<T>::R sigma, double* pa) {
   using R = typename Num<T>::R;
   __shared__ double scratch[kWarps];
-  const uint32_t mask = (p.L >= 32) ? 0xffffffffu : ((1u << p.L) - 1u);
   const uint32_t lo_mask = (1u << p.half) - 1u;
-  const uint32_t wrap_flip = (1u << (p.L - 1)) | 1u;
   const int nbonds = p.periodic ? p.L : p.L - 1;
   const T* __restrict__ xg = reinterpret_cast<const T*>(p.x_all);
   double dot = 0.0;
-  const int64_t chunk = (int64_t)kThreads * ITEMS;
-  for (int64_t base = (int64_t)blockIdx.x * chunk; base < p.n; base += (int64_t)gridDim.x * chunk) {
-    const int64_t first = base + (int64_t)threadIdx.x * ITEMS;
-    if (first >= p.n) continue;
-    uint32_t s = xxz_unrank(p.row0 + first, p.L, p.n_up);
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-      const int64_t r = first + it;
-      if (r >= p.n) break;
-      // anti-parallel bonds: bit i set <=> sites i and i+1 differ (bit L-1 = wrap bond under periodic boundaries)
-      uint32_t d = (s ^ (s >> 1)) & (mask >> 1);
-      if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) d |= (1u << (p.L - 1));
-      const int anti = __popc(d);
-      const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
-      T acc = zero_of(T());
-      while (d) {
-        const int i = __ffs(d) - 1;
-        d &= d - 1;
-        const uint32_t t = s ^ ((i == p.L - 1) ? wrap_flip : (3u << i));
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < p.n; r += (int64_t)gridDim.x * kThreads) {
+    const uint32_t s = __ldg(states + r);
+    // anti-parallel bonds: bit b set <=> sites b and b+1 differ (bit L-1 = wrap bond under periodic boundaries)
+    uint32_t d = (s ^ (s >> 1)) & ((1u << (p.L - 1)) - 1u);
+    if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) d |= (1u << (p.L - 1));
+    T acc = zero_of(T());
+#pragma unroll 2
+    for (int b = 0; b < nbonds; ++b) {
+      if ((d >> b) & 1u) {
+        const uint32_t t = s ^ ((b == p.L - 1) ? ((1u << (p.L - 1)) | 1u) : (3u << b));
         const int64_t jg = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half));
         const int64_t j = jg - p.row0;
         const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + jg);
         acc = add_t(acc, xv);
       }
-      const T xi = x[r];
-      T yi = scale_real(acc, (R)p.jxy2);
-      yi = add_t(yi, scale_real(xi, diag + sigma));
-      y[r] = yi;
-      dot += re_conj_mul(xi, yi);
-      s = gosper_next(s);
     }
+    const R diag = (R)(p.jz4 * (double)(nbonds - 2 * __popc(d)));
+    const T xi = x[r];
+    T yi = scale_real(acc, (R)p.jxy2);
+    yi = add_t(yi, scale_real(xi, diag + sigma));
+    y[r] = yi;
+    dot += re_conj_mul(xi, yi);
   }
   const double t = block_sum(dot, scratch);
   if (threadIdx.x == 0) pa[blockIdx.x] = t;
@@ -97,12 +107,14 @@ struct XxzOpBase : OpBase {
   XxzParams prm;
   uint32_t* d_lo = nullptr;
   uint32_t* d_hi = nullptr;
+  uint32_t* d_states = nullptr;  // basis states of the local block
   void* d_xall = nullptr;  // row-sharded runs: gathered input vector (n_global elements)
   std::vector<size_t> send_off, send_bytes, recv_off, recv_bytes;
   ~XxzOpBase() override {
-    if (d_lo) cudaFree(d_lo);
-    if (d_hi) cudaFree(d_hi);
-    if (d_xall) cudaFree(d_xall);
+    if (d_lo) dev_free(ctx, d_lo);
+    if (d_hi) dev_free(ctx, d_hi);
+    if (d_xall) dev_free(ctx, d_xall);
+    if (d_states) dev_free(ctx, d_states);
   }
   // Row-sharded: every rank sends its block of x to every peer (bit flips on high sites land anywhere in the sector).
   int prepare(const void* x) override {
@@ -114,11 +126,9 @@ struct XxzOpBase : OpBase {
 
 template <class T> struct XxzOp : XxzOpBase {
   int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa) override {
-    constexpr int ITEMS = 4;
-    const int64_t chunk = (int64_t)kThreads * ITEMS;
-    int64_t g = std::min<int64_t>((n_local + chunk - 1) / chunk, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
+    int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_xxz_apply<T, ITEMS><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, prm, (typename Num<T>::R)sigma, pa);
+    k_xxz_apply<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_apply: %s", cudaGetErrorString(e));
@@ -208,6 +218,24 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
   op->prm.n = op->n_local;
   op->prm.row0 = op->row0;
   op->prm.x_all = nullptr;
+  op->bytes = op->n_local * 4;  // the state table is the only stored part of the operator
+  e = dev_malloc(ctx, &op->d_states, sizeof(uint32_t) * (size_t)op->n_local);
+  if (e != cudaSuccess) {
+    delete op;
+    return fail(LLZ_ERR_OOM, "op_create_xxz: state table (%lld entries): %s", (long long)op->n_local, cudaGetErrorString(e));
+  }
+  {
+    const int64_t nchunks = (op->n_local + 31) / 32;
+    const int grid = (int)std::min<int64_t>((nchunks + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 8);
+    k_xxz_states<<<std::max(grid, 1), kThreads, 0, ctx->stream>>>(op->d_states, op->n_local, op->row0, L, n_up);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      delete op;
+      return fail(LLZ_ERR_CUDA, "op_create_xxz: state table kernel: %s", cudaGetErrorString(e));
+    }
+    ctx->launches++;
+  }
   if (ctx->nranks > 1) {
     const size_t es = dtype_size(dtype);
     e = dev_malloc(ctx, &op->d_xall, (size_t)op->n_global * es);
