@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "llz_launch.hpp"
@@ -66,9 +67,13 @@ struct Comm {
   // peer-memory channels for the per-iteration scalar reductions (llz_peer.cuh); G == 0 when unavailable
   void* p2p_local = nullptr;
   void* p2p_peer[kMaxRanks] = {};
-  PeerChannel ch[3];
-  unsigned long long seq[3] = {0, 0, 0};
+  PeerChannel ch[4];
+  unsigned long long seq[4] = {0, 0, 0, 0};
   unsigned int* ticket = nullptr;
+  // halo window: part of the same IPC-mapped allocation, sub-allocated by row-sharded operators for the entries of x
+  // their peers push to them (first-fit free list of [offset, bytes), offsets relative to the window)
+  size_t win_off = 0, win_bytes = 0;
+  std::vector<std::pair<size_t, size_t>> win_free;
 };
 
 #define LLZ_NCCL(expr)                                                                                       \
@@ -156,12 +161,15 @@ static int p2p_setup(llz_ctx_t ctx) {
   const int G = ctx->nranks;
   const char* env = getenv("LLZ_P2P");
   int want = !(env && env[0] == '0');
-  const size_t bytes = channel_bytes(G, kScalarPayload) * 2 + channel_bytes(G, kCoefPayload) + 256;
+  size_t win_bytes = (size_t)256 << 20;
+  if (const char* w = getenv("LLZ_HALO_WINDOW_MB")) win_bytes = (size_t)std::max(0L, atol(w)) << 20;
+  const size_t chan_bytes = (channel_bytes(G, kScalarPayload) * 3 + channel_bytes(G, kCoefPayload) + 256 + 255) / 256 * 256;
+  const size_t bytes = chan_bytes + win_bytes;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   int ok = want;
   if (ok && cudaMalloc(&c->p2p_local, bytes) != cudaSuccess) ok = 0;
-  if (ok && cudaMemset(c->p2p_local, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaMemset(c->p2p_local, 0, chan_bytes) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&mine, c->p2p_local) != cudaSuccess) ok = 0;
   cudaGetLastError();
   struct Rec {
@@ -203,9 +211,12 @@ static int p2p_setup(llz_ctx_t ctx) {
     cudaGetLastError();
     return LLZ_OK;  // NCCL path
   }
-  const int payload[3] = {kScalarPayload, kScalarPayload, kCoefPayload};
+  const int payload[4] = {kScalarPayload, kScalarPayload, kCoefPayload, kScalarPayload};
   size_t off = 256;  // first 256 bytes: status word (+0) and the last-CTA ticket (+64)
-  for (int k = 0; k < 3; ++k) {
+  c->win_off = chan_bytes;
+  c->win_bytes = win_bytes;
+  c->win_free.assign(1, std::make_pair((size_t)0, win_bytes));
+  for (int k = 0; k < 4; ++k) {
     PeerChannel& ch = c->ch[k];
     ch.G = G;
     ch.rank = ctx->rank;
@@ -222,11 +233,54 @@ bool comm_p2p(llz_ctx_t ctx) { return ctx->nranks > 1 && ctx->comm && ctx->comm-
 int comm_coef_capacity(llz_ctx_t ctx) { return comm_p2p(ctx) ? kCoefPayload : 0; }
 unsigned int* comm_ticket(llz_ctx_t ctx) { return comm_p2p(ctx) ? ctx->comm->ticket : nullptr; }
 
-// The channel and the sequence number of its NEXT message (every rank calls this in the same order).
-PeerChannel comm_next_message(llz_ctx_t ctx, int which, unsigned long long* seq) {
+// Halo window of this rank: first-fit sub-allocation (256-byte granularity); returns the offset inside the window or
+// -1 when there is no peer window or no room (the operator then uses the NCCL exchange).
+int64_t comm_window_alloc(llz_ctx_t ctx, size_t bytes) {
+  if (!comm_p2p(ctx) || bytes == 0) return -1;
   Comm* c = ctx->comm;
-  *seq = ++c->seq[which];
-  return c->ch[which];
+  bytes = (bytes + 255) / 256 * 256;
+  for (size_t i = 0; i < c->win_free.size(); ++i) {
+    if (c->win_free[i].second >= bytes) {
+      const size_t off = c->win_free[i].first;
+      c->win_free[i].first += bytes;
+      c->win_free[i].second -= bytes;
+      if (c->win_free[i].second == 0) c->win_free.erase(c->win_free.begin() + i);
+      return (int64_t)off;
+    }
+  }
+  return -1;
+}
+void comm_window_free(llz_ctx_t ctx, int64_t off, size_t bytes) {
+  if (!ctx->comm || off < 0) return;
+  Comm* c = ctx->comm;
+  bytes = (bytes + 255) / 256 * 256;
+  c->win_free.emplace_back((size_t)off, bytes);
+  std::sort(c->win_free.begin(), c->win_free.end());
+  for (size_t i = 0; i + 1 < c->win_free.size();) {  // coalesce neighbours
+    if (c->win_free[i].first + c->win_free[i].second == c->win_free[i + 1].first) {
+      c->win_free[i].second += c->win_free[i + 1].second;
+      c->win_free.erase(c->win_free.begin() + i + 1);
+    } else {
+      ++i;
+    }
+  }
+}
+// Address, valid on THIS GPU, of byte `off` of rank r's halo window.
+void* comm_window_ptr(llz_ctx_t ctx, int r, int64_t off) {
+  Comm* c = ctx->comm;
+  return static_cast<char*>(c->p2p_peer[r]) + c->win_off + off;
+}
+
+// The NEXT message of a channel (every rank calls this in the same order); an unused message (ch.G == 0) when the
+// group has no peer channels.
+PeerMsg comm_next_message(llz_ctx_t ctx, int which) {
+  PeerMsg m;
+  if (!comm_p2p(ctx)) return m;
+  Comm* c = ctx->comm;
+  m.ch = c->ch[which];
+  m.seq = ++c->seq[which];
+  m.ticket = c->ticket;
+  return m;
 }
 
 // Non-zero when a kernel gave up waiting for a peer (the peer process died or diverged).

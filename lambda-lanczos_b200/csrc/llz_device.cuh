@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "llz_peer.cuh"
+
 namespace llz {
 
 constexpr int kThreads = 256;          // every streaming kernel uses 8 warps per CTA
@@ -221,6 +223,33 @@ __device__ __forceinline__ double block_sum_partials(const double* __restrict__ 
   double v = 0.0;
   for (int i = threadIdx.x; i < count; i += kThreads) v += p[i];
   return block_sum(v, scratch);
+}
+
+// Epilogue of every kernel that produces a scalar as per-CTA partials (alpha in the operators, ||u||^2 in the update):
+// stores the CTA's partial; row-sharded with peer channels, the LAST CTA to finish (ticket) also sums the partials and
+// delivers the rank's value to every GPU's inbox — thread p stores to rank p, fences and announces — so no separate
+// reduction kernel or collective sits between the producer and the consumer.  Call with all threads of the CTA.
+__device__ __forceinline__ void finish_scalar(double cta_value, double* partials, const PeerMsg& msg, double* scratch) {
+  if (threadIdx.x == 0) partials[blockIdx.x] = cta_value;
+  if (msg.ch.G == 0) return;
+  __shared__ int last_cta;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(msg.ticket, 1u);
+    last_cta = (t == gridDim.x - 1);
+    if (last_cta) *msg.ticket = 0;
+  }
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  double v = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v += __ldcg(partials + i);
+  v = block_sum(v, scratch);
+  if ((int)threadIdx.x < msg.ch.G) {
+    peer_slot(msg.ch, threadIdx.x, msg.seq, msg.ch.rank)[0] = v;
+    __threadfence_system();
+    peer_announce(msg.ch, threadIdx.x, msg.seq);
+  }
 }
 
 // Transposed warp reduction: each lane holds M partial sums (M a power of two <= 32); afterwards the total of value

@@ -40,7 +40,9 @@ inline size_t dtype_size(int dtype) {
 }
 inline int dtype_nc(int dtype) { return (dtype == LLZ_C64 || dtype == LLZ_C128) ? 2 : 1; }
 
-struct Comm;  // inter-GPU plumbing (llz_comm.cu)
+struct Comm;         // inter-GPU plumbing (llz_comm.cu)
+struct PeerChannel;  // peer-memory message channel (llz_peer.cuh)
+struct PeerMsg;
 
 // Per-kernel device-time accounting (CUDA events on the context's stream), keyed by a short kernel-family name.
 struct ProfEntry {
@@ -114,7 +116,10 @@ struct OpBase {
   // y = A x + sigma x ; per-CTA partials of Re<x,y> into alpha_partials[0..*n_partials) (device), all on ctx->stream.
   // Returns LLZ_OK or an error.  Implementations that cannot fuse the dot leave *n_partials = 0 and the engine runs
   // a separate dot kernel.
-  virtual int apply_fused(const void* x, void* y, double sigma, double* alpha_partials, int* n_partials) = 0;
+  // Row-sharded with peer channels: `alpha_msg` (may be null) asks the kernel to also deliver the rank's alpha to every
+  // GPU (finish_scalar, llz_device.cuh); implementations that leave *n_partials = 0 ignore it.
+  virtual int apply_fused(const void* x, void* y, double sigma, double* alpha_partials, int* n_partials,
+                          const PeerMsg* alpha_msg = nullptr) = 0;
 };
 
 }  // namespace llz
@@ -127,11 +132,13 @@ int comm_allreduce_sum(llz_ctx_t ctx, double* d, int count);
 int comm_allreduce_partials(llz_ctx_t ctx, double* d, int* count);
 void comm_destroy(llz_ctx_t ctx);
 // Peer-memory channels (llz_peer.cuh) set up by llz_ctx_join: 0 = alpha, 1 = beta^2, 2 = projection coefficients
-struct PeerChannel;
 bool comm_p2p(llz_ctx_t ctx);
 int comm_coef_capacity(llz_ctx_t ctx);
 unsigned int* comm_ticket(llz_ctx_t ctx);
 int comm_check_peers(llz_ctx_t ctx);
+int64_t comm_window_alloc(llz_ctx_t ctx, size_t bytes);
+void comm_window_free(llz_ctx_t ctx, int64_t off, size_t bytes);
+void* comm_window_ptr(llz_ctx_t ctx, int rank, int64_t off);
 // Pooled device allocations of a context (llz_ctx.cu)
 int ctx_alloc(llz_ctx_t ctx, size_t bytes, void** out);
 void ctx_free(llz_ctx_t ctx, void* p, size_t bytes);

@@ -221,15 +221,20 @@ __global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
     }
   }
   if (a.msg.ch.G > 0 && a.publish) {
-    __threadfence_system();
+    __shared__ int is_last;
+    if (ty == 0) __threadfence_system();  // the storing threads: their NVLink stores are performed before the ticket
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned int t = atomicAdd(a.ticket, 1u);
-      if (t == gridDim.x - 1) {  // every CTA's stores are visible system-wide: announce
-        *a.ticket = 0;
-        __threadfence_system();
-        for (int p = 0; p < a.msg.ch.G; ++p) peer_announce(a.msg.ch, p, a.msg.seq);
-      }
+      is_last = (t == gridDim.x - 1);
+      if (is_last) *a.ticket = 0;
+    }
+    __syncthreads();
+    // every CTA's stores are visible system-wide: thread p announces to rank p (G release-stores in parallel — one
+    // thread doing all of them would pay G NVLink round trips back to back)
+    if (is_last && (int)threadIdx.x < a.msg.ch.G) {
+      __threadfence_system();
+      peer_announce(a.msg.ch, threadIdx.x, a.msg.seq);
     }
   }
 }
@@ -270,6 +275,7 @@ struct UpdateArgs {
   const void* u2;
   int cu1, cu2;
   PeerMsg coef_msg;  // row-sharded: coefficients = sum over ranks of this message (element col*NC + c)
+  PeerMsg norm_msg;  // row-sharded: deliver sum(pb) group-wide from the last CTA
 };
 
 template <class T, int VPT, bool FULL>
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
   }
   if (a.pb) {
     const double t = block_sum(nrm, scratch);
-    if (tid == 0) a.pb[blockIdx.x] = t;
+    finish_scalar(t, a.pb, a.norm_msg, scratch);
   }
 }
 
@@ -470,6 +476,7 @@ struct RecurrenceArgs {
   double* alpha_out;
   double* pb;
   PeerMsg alpha_msg;
+  PeerMsg norm_msg;
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
@@ -519,7 +526,7 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(R
   }
   if (a.pb) {
     const double t = block_sum(nrm, scratch);
-    if (tid == 0) a.pb[blockIdx.x] = t;
+    finish_scalar(t, a.pb, a.norm_msg, scratch);
   }
 }
 
@@ -659,7 +666,7 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_dot(const T*
   }
 }
 
-template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const T* __restrict__ x, const T* __restrict__ y, int64_t n, double* partials) {
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const T* __restrict__ x, const T* __restrict__ y, int64_t n, double* partials, PeerMsg msg) {
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
   double re = 0.0;
@@ -673,7 +680,7 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const 
     for (int e = 0; e < VEC; ++e) re += re_conj_mul(a.e[e], b.e[e]);
   }
   const double t = block_sum(re, scratch);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+  finish_scalar(t, partials, msg, scratch);
 }
 
 // result[c] = sum_i partials[i*nc + c]; also mirrored to pinned host memory when h_result != null
@@ -821,7 +828,7 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
   a.slot_base = col0 * nc;
   a.wnorm_index = wnorm_index;
   a.publish = publish;
-  a.ticket = comm_ticket(ctx);
+  a.ticket = msg.ticket;
   k_reduce<<<(a.width + 1 + 31) / 32, kThreads, 0, ctx->stream>>>(a);
   return check_launch(ctx, "k_reduce");
 }
@@ -844,7 +851,7 @@ static int update_impl(llz_ctx_t ctx, const UpdateArgs& a, int* grid_out) {
 
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
                   int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
-                  const PeerMsg& coef_msg) {
+                  const PeerMsg& coef_msg, const PeerMsg& norm_msg) {
   if (ncols < 0 || ncols > max_update_cols(dtype)) return fail(LLZ_ERR_INVALID, "update: %d columns per launch", ncols);
   UpdateArgs a;
   a.V = cs.V;
@@ -858,6 +865,7 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
   a.n = n;
   a.coef = coef;
   a.coef_msg = coef_msg;
+  a.norm_msg = norm_partials ? norm_msg : PeerMsg();
   a.pb = norm_partials;
   a.fold = fold.mode;
   a.alpha = fold.alpha_out;
@@ -906,6 +914,7 @@ int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, c
   a.beta_prev = fold.beta_prev;
   a.alpha_out = fold.alpha_out;
   a.alpha_msg = fold.alpha_msg;
+  a.norm_msg = norm_partials ? fold.norm_msg : PeerMsg();
   a.pb = norm_partials;
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
@@ -960,11 +969,12 @@ int launch_dot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n
   return check_launch(ctx, "k_dot");
 }
 
-int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out) {
+int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out,
+                 const PeerMsg& msg) {
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
     const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
-    k_redot<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)a, (const T*)b, n, partials);
+    k_redot<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)a, (const T*)b, n, partials, msg);
     *grid_out = grid;
   });
   return check_launch(ctx, "k_redot");

@@ -155,19 +155,9 @@ int ensure_ph(llz_krylov_t kry, size_t doubles) {
   return LLZ_OK;
 }
 
-// One classical Gram-Schmidt pass of `w` against cs: project -> reduce -> update (in place).  With an empty column
-// set only the update kernel runs (it then just produces the norm partials of w).
-// Group-wide scalar held as per-CTA partials (alpha after the operator, ||u||^2 after the update): with peer channels
-// one tiny kernel delivers this rank's sum to every inbox and the consumer adds the G parts in its prologue; otherwise
-// the partials are folded and all-reduced over NCCL (count becomes 1).  Single rank: nothing to do.
-int share_scalar(llz_ctx_t ctx, int channel, double* partials, int* count, PeerMsg* msg) {
-  *msg = PeerMsg();
-  if (ctx->nranks == 1) return LLZ_OK;
-  if (comm_p2p(ctx)) {
-    msg->ch = comm_next_message(ctx, channel, &msg->seq);
-    ProfScope ps(ctx, "exchange", 0.0);
-    return launch_push_scalar(ctx, partials, *count, *msg);
-  }
+// NCCL path only (no peer channels): fold the per-CTA partials of a group-wide scalar and all-reduce them.
+int allreduce_scalar(llz_ctx_t ctx, double* partials, int* count) {
+  if (ctx->nranks == 1 || comm_p2p(ctx)) return LLZ_OK;
   ProfScope ps(ctx, "exchange", 0.0);
   return comm_allreduce_partials(ctx, partials, count);
 }
@@ -177,6 +167,8 @@ int share_scalar(llz_ctx_t ctx, int channel, double* partials, int* count, PeerM
 // ||w'||^2 of this pass can be read (peer message element or kry->d_misc[1]).
 int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, bool want_norm, int* norm_grid,
              PeerMsg* wnorm_msg = nullptr, int* wnorm_index = nullptr) {
+  // (row-sharded with peer channels: fold.norm_msg, if used, is delivered by the update kernel that writes the norm
+  //  partials; the coefficients travel as one message of the coefficient channel)
   llz_ctx_t ctx = kry->ctx;
   const int nc = dtype_nc(kry->dtype);
   const int total = cs.ncols();
@@ -186,7 +178,7 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
   if (total > 0) {
     const bool peer = comm_p2p(ctx) && total * nc + 1 <= comm_coef_capacity(ctx);
     if (peer) {
-      coef_msg.ch = comm_next_message(ctx, kChanCoef, &coef_msg.seq);
+      coef_msg = comm_next_message(ctx, kChanCoef);
       if (wnorm_msg) *wnorm_msg = coef_msg;
       if (wnorm_index) *wnorm_index = total * nc;
     }
@@ -220,9 +212,10 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
     const int cols = std::min(uchunk, generic - c0);
     const bool last = c0 + cols >= generic;
     Fold f = (c0 == 0) ? fold : Fold();
+    f.norm_msg = fold.norm_msg;
     ProfScope ps(ctx, "update", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + f.mode + 2));
     LLZ_TRY(launch_update(ctx, kry->dtype, cs, c0, cols, w, w, kry->n, kry->d_coef, f,
-                          (last && want_norm) ? kry->d_pb : nullptr, norm_grid, coef_msg));
+                          (last && want_norm) ? kry->d_pb : nullptr, norm_grid, coef_msg, fold.norm_msg));
     c0 += cols;
   } while (c0 < generic);
   return LLZ_OK;
@@ -435,9 +428,10 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   int grid = 0;
   // the start vector may lie almost inside span(locked): orthogonalise twice ("twice is enough")
   if (kry->nq > 0) LLZ_TRY(cgs_pass(kry, cs, u0, nofold, false, &grid));
-  LLZ_TRY(cgs_pass(kry, cs, u0, nofold, true, &grid));
   ScalarSink sink;
-  LLZ_TRY(share_scalar(ctx, kChanBeta, kry->d_pb, &grid, &sink.beta_msg));
+  nofold.norm_msg = sink.beta_msg = comm_next_message(ctx, kChanBeta);
+  LLZ_TRY(cgs_pass(kry, cs, u0, nofold, true, &grid));
+  LLZ_TRY(allreduce_scalar(ctx, kry->d_pb, &grid));
   sink.beta_out = kry->d_misc;
   sink.h_beta = kry->h_misc;
   {
@@ -463,16 +457,17 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
 
   int npa = 0;
   LLZ_TRY(op->impl->prepare(x));
+  Fold fold;
+  fold.alpha_msg = comm_next_message(ctx, kChanAlpha);  // delivered by the last CTA of the kernel that computes <x, Ax>
   {
     ProfScope ps(ctx, "spmv", (double)op->impl->bytes + (double)kry->n * (double)dtype_size(kry->dtype) * 2);
-    LLZ_TRY(op->impl->apply_fused(x, y, sigma, kry->d_pa, &npa));
+    LLZ_TRY(op->impl->apply_fused(x, y, sigma, kry->d_pa, &npa, &fold.alpha_msg));
   }
   if (npa == 0) {
     ProfScope ps(ctx, "dot", (double)kry->n * (double)dtype_size(kry->dtype) * 2);
-    LLZ_TRY(launch_redot(ctx, kry->dtype, x, y, kry->n, kry->d_pa, &npa));
+    LLZ_TRY(launch_redot(ctx, kry->dtype, x, y, kry->n, kry->d_pa, &npa, fold.alpha_msg));
   }
-  Fold fold;
-  LLZ_TRY(share_scalar(ctx, kChanAlpha, kry->d_pa, &npa, &fold.alpha_msg));
+  LLZ_TRY(allreduce_scalar(ctx, kry->d_pa, &npa));
   fold.mode = (k == 1) ? 1 : 2;
   fold.alpha_partials = kry->d_pa;
   fold.n_partials = npa;
@@ -481,7 +476,9 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
 
   int grid = 0;
   ScalarSink sink;
+  sink.beta_msg = comm_next_message(ctx, kChanBeta);  // delivered by the kernel that writes the norm partials
   if (orth == LLZ_ORTH_RECURRENCE) {
+    fold.norm_msg = sink.beta_msg;
     ProfScope ps(ctx, "recurrence", (double)kry->n * (double)dtype_size(kry->dtype) * (2 + fold.mode));
     LLZ_TRY(launch_recurrence(ctx, kry->dtype, y, kry->col(k - 1), k >= 2 ? kry->col(k - 2) : nullptr, y, kry->n, fold,
                               kry->d_pb, &grid));
@@ -492,13 +489,15 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     cs.nv = (int)k;
     cs.Q = (const void* const*)kry->d_qptrs;
     cs.nq = kry->nq;
-    LLZ_TRY(cgs_pass(kry, cs, y, fold, true, &grid, &sink.wnorm_msg, &sink.wnorm_index));
+    if (orth != LLZ_ORTH_FULL_TWICE) fold.norm_msg = sink.beta_msg;
+    LLZ_TRY(cgs_pass(kry, cs, y, fold, orth != LLZ_ORTH_FULL_TWICE, &grid, &sink.wnorm_msg, &sink.wnorm_index));
     if (orth == LLZ_ORTH_FULL_TWICE) {
       Fold nofold;
+      nofold.norm_msg = sink.beta_msg;
       LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
     }
   }
-  LLZ_TRY(share_scalar(ctx, kChanBeta, kry->d_pb, &grid, &sink.beta_msg));
+  LLZ_TRY(allreduce_scalar(ctx, kry->d_pb, &grid));
   sink.beta_out = kry->d_beta + (k - 1);
   sink.alpha_in = kry->d_alpha + (k - 1);
   sink.h_alpha = kry->h_alpha + (k - 1);
@@ -551,9 +550,10 @@ int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink) {
   cs.nq = kry->nq;
   Fold nofold;
   int grid = 0;
-  LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
   ScalarSink sink;
-  LLZ_TRY(share_scalar(ctx, kChanBeta, kry->d_pb, &grid, &sink.beta_msg));
+  nofold.norm_msg = sink.beta_msg = comm_next_message(ctx, kChanBeta);
+  LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
+  LLZ_TRY(allreduce_scalar(ctx, kry->d_pb, &grid));
   sink.beta_out = kry->d_misc;
   sink.h_beta = kry->h_misc;
   {

@@ -5,16 +5,11 @@
 
 namespace llz {
 
-// The channel and the sequence number of its NEXT message (llz_comm.cu; every rank calls this in the same order).
-PeerChannel comm_next_message(llz_ctx_t ctx, int which, unsigned long long* seq);
-enum { kChanAlpha = 0, kChanBeta = 1, kChanCoef = 2 };
+// The NEXT message of a peer channel (llz_comm.cu; every rank calls this in the same order); unused (ch.G == 0) when
+// the context has no peer channels.
+PeerMsg comm_next_message(llz_ctx_t ctx, int which);
+enum { kChanAlpha = 0, kChanBeta = 1, kChanCoef = 2, kChanHalo = 3 };
 
-// A group-wide scalar or coefficient vector delivered through a peer-memory channel: message `seq` of `ch`.
-// ch.G == 0 means "not used": the consumer reads this rank's own device memory instead.
-struct PeerMsg {
-  PeerChannel ch;
-  unsigned long long seq = 0;
-};
 
 // The set of orthonormal columns a vector is projected on: `nq` separately allocated vectors (device pointer table)
 // followed by `nv` contiguous columns of the Krylov basis.  Column index space: [0,nq) = Q, [nq,nq+nv) = V.
@@ -36,6 +31,8 @@ struct Fold {
   const double* beta_prev = nullptr;    // device address of beta_{k-2}
   double* alpha_out = nullptr;          // device address receiving alpha_{k-1}
   PeerMsg alpha_msg;                    // row-sharded: alpha = sum over ranks of this message instead of the partials
+  PeerMsg norm_msg;                     // row-sharded: the kernel that produces the norm partials (update / recurrence)
+                                        // also delivers their sum as this message (consumed by scale_by_norm)
 };
 
 // Where scale_by_norm publishes the iteration's scalars.
@@ -74,7 +71,7 @@ int launch_push_scalar(llz_ctx_t ctx, const double* partials, int count, const P
 // If norm_partials != null, per-CTA partials of ||out||^2.
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
                   int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
-                  const PeerMsg& coef_msg = PeerMsg());
+                  const PeerMsg& coef_msg = PeerMsg(), const PeerMsg& norm_msg = PeerMsg());
 // x *= 1/sqrt(sum partials); publishes beta (and alpha) per `sink`.  Leaves x untouched when the norm is not > 0.
 int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
                          const ScalarSink& sink);
@@ -89,7 +86,8 @@ int launch_combine(llz_ctx_t ctx, int dtype, const void* V, int64_t ld, int col0
 // partials of <a,b> (NC doubles per CTA, interleaved) and of Re<a,b> only
 int launch_dot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out);
 // partials of Re<a,b> only, one double per CTA (alpha when the operator cannot fuse the dot)
-int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out);
+int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out,
+                 const PeerMsg& msg = PeerMsg());
 // result[0..NC) = sum of partials (single CTA)
 int launch_sum_partials(llz_ctx_t ctx, const double* partials, int count, int nc, double* result, double* h_result);
 int launch_scale(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double a[2]);

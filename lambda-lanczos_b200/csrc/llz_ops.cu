@@ -36,12 +36,44 @@ template <class T> __global__ void __launch_bounds__(kThreads) k_pack(const T* _
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads) out[i] = __ldg(x + idx[i]);
 }
 
+// Peer-memory halo exchange: instead of pack -> ncclSend/ncclRecv, every rank stores the entries its peers need straight
+// into their halo buffers (sub-allocations of the IPC-mapped window, double-buffered by message parity) and the last
+// CTA announces the message; the SpMV kernels wait for the G announcements in their prologue.
+struct HaloPush {
+  int G = 0;
+  long long start[kMaxRanks + 1] = {};  // send entries [start[q], start[q+1]) go to rank q
+  void* dst[kMaxRanks] = {};            // where they go (address of rank q's halo segment for this rank, mapped here)
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_halo_push(const T* __restrict__ x, const int32_t* __restrict__ idx, long long n_send, HaloPush hp, PeerMsg msg) {
+  __shared__ int last_cta;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_send; i += (long long)gridDim.x * kThreads) {
+    int q = 0;
+    while (i >= hp.start[q + 1]) ++q;
+    reinterpret_cast<T*>(hp.dst[q])[i - hp.start[q]] = __ldg(x + idx[i]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(msg.ticket, 1u);
+    last_cta = (t == gridDim.x - 1);
+    if (last_cta) *msg.ticket = 0;
+  }
+  __syncthreads();
+  if (last_cta && (int)threadIdx.x < msg.ch.G) {
+    __threadfence_system();
+    peer_announce(msg.ch, threadIdx.x, msg.seq);
+  }
+}
+
 template <class T, class IDX, int LPR>
 __global__ void __launch_bounds__(kThreads, 4)
     k_csr_spmv_dot(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
                    const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
-                   typename Num<T>::R sigma, double* pa) {
+                   typename Num<T>::R sigma, double* pa, PeerMsg msg, PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
+  if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);  // the peers' entries of x have landed in `halo`
   constexpr int ROWS = kThreads / LPR;
   const int tid = threadIdx.x;
   const int sub = tid % LPR;
@@ -64,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 4)
     }
   }
   const double t = block_sum(dot, scratch);
-  if (tid == 0) pa[blockIdx.x] = t;
+  finish_scalar(t, pa, msg, scratch);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -79,8 +111,9 @@ template <class T, class IDX>
 __global__ void __launch_bounds__(kThreads, 4)
     k_csr_stream_dot(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
                      const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
-                     typename Num<T>::R sigma, double* pa, int R, int cap) {
+                     typename Num<T>::R sigma, double* pa, int R, int cap, PeerMsg msg, PeerMsg halo_msg) {
   extern __shared__ __align__(16) unsigned char smem_s[];
+  if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   T* prod = reinterpret_cast<T*>(smem_s);
   IDX* rp = reinterpret_cast<IDX*>(prod + cap);
   __shared__ double scratch[kWarps];
@@ -108,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 4)
     __syncthreads();
   }
   const double t = block_sum(dot, scratch);
-  if (tid == 0) pa[blockIdx.x] = t;
+  finish_scalar(t, pa, msg, scratch);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -188,8 +221,10 @@ template <class T>
 __global__ void __launch_bounds__(kThreads, 3)
     k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
                     const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
-                    T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa) {
+                    T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
+                    PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
+  if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   constexpr int U = 2;  // slices per warp step
   const int lane = threadIdx.x & 31;
   double dot = 0.0;
@@ -250,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 3)
     }
   }
   const double t = block_sum(dot, scratch);
-  if (threadIdx.x == 0) pa[blockIdx.x] = t;
+  finish_scalar(t, pa, msg, scratch);
 }
 
 template <class T> struct CsrOp : OpBase {
@@ -269,6 +304,12 @@ template <class T> struct CsrOp : OpBase {
   T* d_sendbuf = nullptr;        // [n_send] packed entries of the local block, grouped by requesting peer
   int32_t* d_send_idx = nullptr; // [n_send] local indices to pack
   std::vector<size_t> send_off, send_bytes, recv_off, recv_bytes;
+  // peer-memory variant: halo buffers live in this rank's IPC window (two copies, by message parity)
+  int64_t win_off = -1;
+  HaloPush push;                    // destinations for parity 0; parity 1 is + push_stride[q] bytes
+  size_t push_stride[kMaxRanks] = {};
+  const T* cur_halo = nullptr;      // what the next apply reads
+  PeerMsg cur_halo_msg;             // ... after waiting for this message
   // SELL-C-sigma storage (convert_to_sell releases the CSR arrays)
   bool sell = false;
   int sell_sigma = 1;
@@ -287,6 +328,7 @@ template <class T> struct CsrOp : OpBase {
     if (d_colidx) dev_free(ctx, d_colidx);
     if (d_vals) dev_free(ctx, d_vals);
     if (d_halo) dev_free(ctx, d_halo);
+    if (win_off >= 0) comm_window_free(ctx, win_off, 2 * (size_t)std::max<int64_t>(n_halo, 1) * sizeof(T));
     if (d_sendbuf) dev_free(ctx, d_sendbuf);
     if (d_send_idx) dev_free(ctx, d_send_idx);
   }
@@ -294,7 +336,26 @@ template <class T> struct CsrOp : OpBase {
 
   // Bring the remote entries of x this block references into d_halo (no-op for a single rank).
   int prepare(const void* x) override {
-    if (ctx->nranks == 1 || (n_halo == 0 && n_send == 0)) return LLZ_OK;
+    cur_halo = d_halo;
+    cur_halo_msg = PeerMsg();
+    if (ctx->nranks == 1) return LLZ_OK;
+    if (win_off >= 0) {  // peer-memory exchange (every rank of the group takes this branch together)
+      ProfScope ps(ctx, "halo", (double)(n_halo + n_send) * sizeof(T));
+      PeerMsg m = comm_next_message(ctx, kChanHalo);
+      HaloPush hp = push;
+      if (m.seq & 1ull)
+        for (int q = 0; q < hp.G; ++q) hp.dst[q] = static_cast<char*>(hp.dst[q]) + push_stride[q];
+      const int64_t g = std::max<int64_t>(1, std::min<int64_t>((n_send + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 2));
+      k_halo_push<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, d_send_idx, (long long)n_send, hp, m);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_halo_push: %s", cudaGetErrorString(e));
+      ctx->launches++;
+      cur_halo = reinterpret_cast<const T*>(static_cast<char*>(comm_window_ptr(ctx, ctx->rank, win_off)) +
+                                            ((m.seq & 1ull) ? (size_t)std::max<int64_t>(n_halo, 1) * sizeof(T) : 0));
+      cur_halo_msg = m;
+      return LLZ_OK;
+    }
+    if (n_halo == 0 && n_send == 0) return LLZ_OK;
     ProfScope ps(ctx, "halo", (double)(n_halo + n_send) * sizeof(T));
     if (n_send > 0) {
       const int64_t g = std::min<int64_t>((n_send + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 4);
@@ -307,13 +368,14 @@ template <class T> struct CsrOp : OpBase {
                          recv_bytes.data());
   }
 
-  template <class IDX, int LPR> int launch(const void* x, void* y, double sigma, double* pa, int* npa) {
+  template <class IDX, int LPR> int launch(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
     constexpr int ROWS = kThreads / LPR;
     int64_t blocks = (n_local + ROWS - 1) / ROWS;
     int64_t g = std::min<int64_t>(blocks, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
     k_csr_spmv_dot<T, IDX, LPR><<<(int)g, kThreads, 0, ctx->stream>>>(
-        (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, d_halo, nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa);
+        (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, cur_halo, nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa, msg,
+        cur_halo_msg);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_csr_spmv_dot: %s", cudaGetErrorString(e));
@@ -321,18 +383,18 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
 
-  template <class IDX> int launch_lpr(const void* x, void* y, double sigma, double* pa, int* npa) {
+  template <class IDX> int launch_lpr(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
     switch (lpr) {
-      case 1: return launch<IDX, 1>(x, y, sigma, pa, npa);
-      case 2: return launch<IDX, 2>(x, y, sigma, pa, npa);
-      case 4: return launch<IDX, 4>(x, y, sigma, pa, npa);
-      case 8: return launch<IDX, 8>(x, y, sigma, pa, npa);
-      case 16: return launch<IDX, 16>(x, y, sigma, pa, npa);
-      default: return launch<IDX, 32>(x, y, sigma, pa, npa);
+      case 1: return launch<IDX, 1>(x, y, sigma, pa, npa, msg);
+      case 2: return launch<IDX, 2>(x, y, sigma, pa, npa, msg);
+      case 4: return launch<IDX, 4>(x, y, sigma, pa, npa, msg);
+      case 8: return launch<IDX, 8>(x, y, sigma, pa, npa, msg);
+      case 16: return launch<IDX, 16>(x, y, sigma, pa, npa, msg);
+      default: return launch<IDX, 32>(x, y, sigma, pa, npa, msg);
     }
   }
 
-  template <class IDX> int launch_stream(const void* x, void* y, double sigma, double* pa, int* npa) {
+  template <class IDX> int launch_stream(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
     const size_t smem = (size_t)stream_cap * sizeof(T) + (size_t)(stream_rows + 1) * sizeof(IDX);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k_csr_stream_dot<T, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -341,9 +403,9 @@ template <class T> struct CsrOp : OpBase {
     const int64_t blocks = (n_local + stream_rows - 1) / stream_rows;
     int64_t g = std::min<int64_t>(blocks, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_csr_stream_dot<T, IDX><<<(int)g, kThreads, smem, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, d_halo,
+    k_csr_stream_dot<T, IDX><<<(int)g, kThreads, smem, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, cur_halo,
                                                                      nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa,
-                                                                     stream_rows, stream_cap);
+                                                                     stream_rows, stream_cap, msg, cur_halo_msg);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_csr_stream_dot: %s", cudaGetErrorString(e));
@@ -351,12 +413,12 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
 
-  int launch_sell(const void* x, void* y, double sigma, double* pa, int* npa) {
+  int launch_sell(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
     const int64_t per_cta = kWarps * 2;  // slices one CTA covers per step
     int64_t g = std::min<int64_t>((n_slices + per_cta - 1) / per_cta, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_sell_spmv_dot<T><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, d_halo, nloc32(), (T*)y,
-                                                            n_local, n_slices, (typename Num<T>::R)sigma, pa);
+    k_sell_spmv_dot<T><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(), (T*)y,
+                                                            n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_sell_spmv_dot: %s", cudaGetErrorString(e));
@@ -452,10 +514,11 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
 
-  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa) override {
-    if (sell) return launch_sell(x, y, sigma, pa, npa);
-    if (stream_rows > 0) return idx32 ? launch_stream<int32_t>(x, y, sigma, pa, npa) : launch_stream<int64_t>(x, y, sigma, pa, npa);
-    return idx32 ? launch_lpr<int32_t>(x, y, sigma, pa, npa) : launch_lpr<int64_t>(x, y, sigma, pa, npa);
+  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg* alpha_msg) override {
+    const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
+    if (sell) return launch_sell(x, y, sigma, pa, npa, msg);
+    if (stream_rows > 0) return idx32 ? launch_stream<int32_t>(x, y, sigma, pa, npa, msg) : launch_stream<int64_t>(x, y, sigma, pa, npa, msg);
+    return idx32 ? launch_lpr<int32_t>(x, y, sigma, pa, npa, msg) : launch_lpr<int64_t>(x, y, sigma, pa, npa, msg);
   }
 };
 
@@ -516,6 +579,36 @@ static int plan_sharded_csr(CsrOp<T>* op, int64_t row0, const int64_t* rowptr, c
     for (int64_t i = 0; i < n_halo; ++i) {
       while (halo_cols[i] >= bounds[owner + 1]) ++owner;
       req[(size_t)i] = (int32_t)(halo_cols[i] - bounds[owner]);
+    }
+  }
+  // Peer-memory exchange: every rank reserves 2 x n_halo entries in its IPC window; it is used only if ALL ranks got
+  // their space (the offsets are all-gathered, so the decision is the same everywhere).
+  {
+    const size_t mine_bytes = 2 * (size_t)std::max<int64_t>(n_halo, 1) * sizeof(T);
+    int64_t my_off = comm_window_alloc(ctx, mine_bytes);
+    std::vector<int64_t> offs((size_t)G, -1);
+    LLZ_TRY(comm_allgather_host(ctx, &my_off, offs.data(), sizeof(int64_t)));
+    bool all = true;
+    for (int r = 0; r < G; ++r) all = all && offs[(size_t)r] >= 0;
+    if (!all) {
+      if (my_off >= 0) comm_window_free(ctx, my_off, mine_bytes);
+    } else {
+      op->win_off = my_off;
+      op->push.G = G;
+      int64_t st = 0;
+      for (int q = 0; q < G; ++q) {
+        op->push.start[q] = st;
+        st += need_all[(size_t)q * G + me];
+        // my segment inside rank q's halo buffer starts after what q receives from the ranks below me
+        int64_t before = 0, q_halo = 0;
+        for (int pp = 0; pp < G; ++pp) {
+          if (pp < me) before += need_all[(size_t)q * G + pp];
+          q_halo += need_all[(size_t)q * G + pp];
+        }
+        op->push.dst[q] = static_cast<char*>(comm_window_ptr(ctx, q, offs[(size_t)q])) + (size_t)before * sizeof(T);
+        op->push_stride[q] = (size_t)std::max<int64_t>(q_halo, 1) * sizeof(T);
+      }
+      op->push.start[G] = st;
     }
   }
   int32_t* d_req = nullptr;
@@ -657,7 +750,7 @@ struct CallbackOp : OpBase {
   llz_apply_fn fn = nullptr;
   void* user = nullptr;
   bool overwrites = false;
-  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa) override {
+  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg*) override {
     (void)pa;
     *npa = 0;
     if (!overwrites) {

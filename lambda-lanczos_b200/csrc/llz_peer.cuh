@@ -31,6 +31,14 @@ struct PeerChannel {
   double* inbox[kMaxRanks] = {};
 };
 
+// A group-wide scalar or coefficient vector delivered through a channel: message `seq` of `ch`.
+// ch.G == 0 means "not used": the consumer reads this rank's own device memory instead.
+struct PeerMsg {
+  PeerChannel ch;
+  unsigned long long seq = 0;
+  unsigned int* ticket = nullptr;  // device counter for last-CTA detection in the producing kernel
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ double* peer_slot(const PeerChannel& ch, int owner, unsigned long long seq, int src) {
   return ch.inbox[owner] + ((size_t)(seq & 1ull) * ch.G + src) * ch.payload;

@@ -62,35 +62,51 @@ __global__ void __launch_bounds__(kThreads) k_xxz_states(uint32_t* __restrict__ 
 }
 
 // One thread per basis state, consecutive threads on consecutive states, and a loop over the BONDS that is uniform
-// across the warp: for a given bond the 32 lanes flip the same two bits of 32 consecutive states, so their targets are
-// (nearly) consecutive ranks — exactly consecutive whenever the lanes share the half of the bit string the bond does
-// not touch, because rank = lo[low half] + hi[high half] — and the x gathers coalesce into a few 128-byte lines
-// instead of 32 separate sectors.  The state itself comes from a 4-byte-per-row table (A_bytes = 4 n).
+// across the warp.  The rank of the flipped state needs no table: in the combinatorial number system
+// rank(s) = sum_j C(p_j, j) (p_j = position of the j-th set bit), exchanging the adjacent bits (b, b+1) moves one set
+// bit by one place and changes the rank by exactly
+//        +C(b, c)  if bit b was the set one,   -C(b, c)  if bit b+1 was,      c = popcount(s & ((1 << b) - 1)),
+// a shared-memory lookup in Pascal's triangle.  For a given bond the 32 lanes hold 32 consecutive states, which share
+// all but their lowest bits: on high bonds c — hence the offset — is the same in every lane and the x gather is one
+// contiguous 256-byte read; on low bonds the offsets are a few hundred elements at most and hit L1.  Only the periodic
+// wrap bond (bits L-1 and 0) re-ranks through the two Lin tables.  The state itself comes from a 4-byte-per-row table
+// (A_bytes = 4 n).
 template <class T>
 __global__ void __launch_bounds__(kThreads, 4)
     k_xxz_apply(const T* __restrict__ x, T* __restrict__ y, const uint32_t* __restrict__ states, XxzParams p,
-                typename Num<T>::R sigma, double* pa) {
+                typename Num<T>::R sigma, double* pa, PeerMsg msg) {
   using R = typename Num<T>::R;
   __shared__ double scratch[kWarps];
+  __shared__ uint32_t pascal[32][33];  // pascal[b][c] = C(b, c); the padding column spreads rows over the banks
+  for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[i >> 5][i & 31] = (uint32_t)c_binom[i >> 5][i & 31];
+  __syncthreads();
   const uint32_t lo_mask = (1u << p.half) - 1u;
   const int nbonds = p.periodic ? p.L : p.L - 1;
+  const int inner = p.L - 1;  // bonds (b, b+1) that stay inside the bit string
   const T* __restrict__ xg = reinterpret_cast<const T*>(p.x_all);
   double dot = 0.0;
   for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < p.n; r += (int64_t)gridDim.x * kThreads) {
     const uint32_t s = __ldg(states + r);
     // anti-parallel bonds: bit b set <=> sites b and b+1 differ (bit L-1 = wrap bond under periodic boundaries)
     uint32_t d = (s ^ (s >> 1)) & ((1u << (p.L - 1)) - 1u);
-    if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) d |= (1u << (p.L - 1));
     T acc = zero_of(T());
-#pragma unroll 2
-    for (int b = 0; b < nbonds; ++b) {
+#pragma unroll 4
+    for (int b = 0; b < inner; ++b) {
       if ((d >> b) & 1u) {
-        const uint32_t t = s ^ ((b == p.L - 1) ? ((1u << (p.L - 1)) | 1u) : (3u << b));
-        const int64_t jg = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half));
-        const int64_t j = jg - p.row0;
-        const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + jg);
+        const int c = __popc(s & ((1u << b) - 1u));
+        const int64_t delta = (int64_t)pascal[b][c];
+        const int64_t j = ((s >> b) & 1u) ? r + delta : r - delta;  // local index of the target (may leave the block)
+        const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + (j + p.row0));
         acc = add_t(acc, xv);
       }
+    }
+    if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) {
+      d |= (1u << (p.L - 1));
+      const uint32_t t = s ^ ((1u << (p.L - 1)) | 1u);
+      const int64_t jg = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half));
+      const int64_t j = jg - p.row0;
+      const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + jg);
+      acc = add_t(acc, xv);
     }
     const R diag = (R)(p.jz4 * (double)(nbonds - 2 * __popc(d)));
     const T xi = x[r];
@@ -100,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 4)
     dot += re_conj_mul(xi, yi);
   }
   const double t = block_sum(dot, scratch);
-  if (threadIdx.x == 0) pa[blockIdx.x] = t;
+  finish_scalar(t, pa, msg, scratch);
 }
 
 struct XxzOpBase : OpBase {
@@ -125,10 +141,11 @@ struct XxzOpBase : OpBase {
 };
 
 template <class T> struct XxzOp : XxzOpBase {
-  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa) override {
+  int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg* alpha_msg) override {
     int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_xxz_apply<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa);
+    k_xxz_apply<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa,
+                                                        alpha_msg ? *alpha_msg : PeerMsg());
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_apply: %s", cudaGetErrorString(e));

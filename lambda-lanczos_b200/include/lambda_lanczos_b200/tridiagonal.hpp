@@ -68,18 +68,45 @@ inline Bounds<R> gerschgorin(const R* a, const R* b, size_t m) {
 // State carried from one Lanczos iteration to the next so that brackets can be warm-started.
 template <typename R>
 struct ExtremeState {
-  std::vector<R> prev;  // extreme eigenvalues of T_{m-1}, in the order they were returned
+  std::vector<R> prev;   // extreme eigenvalues of T_{m-1}, in the order they were returned
+  std::vector<R> delta;  // how far each of them moved in the last iteration (predicts the next move)
   size_t prev_m = 0;
   bool prev_max = false;
   void clear() {
     prev.clear();
+    delta.clear();
     prev_m = 0;
   }
 };
 
+// Sturm counts at up to 16 shifts in ONE sweep over T: the recurrences of different shifts are independent, so their
+// divisions pipeline (a single recurrence is bound by the divider's latency).  bb[i] = b[i]^2.
+template <typename R>
+inline void sturm_counts_batched(const R* a, const R* bb, size_t m, const R* x, size_t nx, R pivmin, size_t* cnt) {
+  constexpr size_t kW = 16;
+  R q[kW];
+  for (size_t r = 0; r < nx; ++r) {
+    q[r] = a[0] - x[r];
+    if (std::abs(q[r]) < pivmin) q[r] = -pivmin;
+    cnt[r] = q[r] < 0 ? 1 : 0;
+  }
+  for (size_t i = 1; i < m; ++i) {
+    const R b2 = bb[i - 1];
+    const R ai = a[i];
+    for (size_t r = 0; r < nx; ++r) {
+      R t = ai - x[r] - b2 / q[r];
+      t = (std::abs(t) < pivmin) ? -pivmin : t;
+      q[r] = t;
+      cnt[r] += t < 0 ? 1 : 0;
+    }
+  }
+}
+
 // The `nroot` smallest (find_max = false, ascending) or largest (find_max = true, descending) eigenvalues of T_m —
-// what lambda_lanczos.hpp:264-277 extracts from the full spectrum.  All roots are bisected together (the Sturm
-// recurrences of different roots are independent, which fills the divider pipeline).
+// what lambda_lanczos.hpp:264-277 extracts from the full spectrum.  Sturm bisection with all roots advanced together;
+// from the second call on the brackets are predicted from the previous iteration (Cauchy interlacing bounds the move
+// of every extreme value, and its last move predicts the size of the next one), checked by one batched Sturm sweep
+// and widened when the prediction fails — so a converging value costs a handful of sweeps, not ~50.
 template <typename R>
 inline void extreme_eigenvalues(const R* a, const R* b, size_t m, size_t nroot, bool find_max, std::vector<R>& out,
                                 ExtremeState<R>* state = nullptr) {
@@ -90,6 +117,7 @@ inline void extreme_eigenvalues(const R* a, const R* b, size_t m, size_t nroot, 
     out[0] = a[0];
     if (state) {
       state->prev = out;
+      state->delta.assign(1, std::numeric_limits<R>::infinity());
       state->prev_m = 1;
       state->prev_max = find_max;
     }
@@ -97,7 +125,9 @@ inline void extreme_eigenvalues(const R* a, const R* b, size_t m, size_t nroot, 
   }
   const Bounds<R> g = gerschgorin(a, b, m);
   const R eps = std::numeric_limits<R>::epsilon();
-  constexpr size_t kMaxBatch = 16;
+  constexpr size_t kMaxBatch = 8;
+  std::vector<R> bb(m > 1 ? m - 1 : 1);
+  for (size_t i = 0; i + 1 < m; ++i) bb[i] = b[i] * b[i];
   std::vector<R> lo(nroot), hi(nroot);
   std::vector<size_t> want(nroot);  // ascending index of each requested root
   for (size_t r = 0; r < nroot; ++r) {
@@ -105,31 +135,65 @@ inline void extreme_eigenvalues(const R* a, const R* b, size_t m, size_t nroot, 
     lo[r] = g.lo;
     hi[r] = g.hi;
   }
-  // Warm start (Cauchy interlacing between T_{m-1} and T_m): the r-th smallest value can only move down and stays
-  // above the (r-1)-th smallest of T_{m-1}; mirrored for the largest values.  Verified below, so a stale state is safe.
+  const R slack = 4 * eps * g.norm;
   if (state && state->prev_m + 1 == m && state->prev_max == find_max && !state->prev.empty()) {
-    for (size_t r = 0; r < nroot; ++r) {
-      if (!find_max) {
-        if (r < state->prev.size()) hi[r] = std::min(g.hi, state->prev[r] + 4 * eps * g.norm);
-        if (r >= 1 && r - 1 < state->prev.size()) lo[r] = std::max(g.lo, state->prev[r - 1] - 4 * eps * g.norm);
-      } else {
-        if (r < state->prev.size()) lo[r] = std::max(g.lo, state->prev[r] - 4 * eps * g.norm);
-        if (r >= 1 && r - 1 < state->prev.size()) hi[r] = std::min(g.hi, state->prev[r - 1] + 4 * eps * g.norm);
+    const std::vector<R>& pv = state->prev;
+    for (size_t r0 = 0; r0 < nroot; r0 += kMaxBatch) {
+      const size_t nb = std::min(kMaxBatch, nroot - r0);
+      // interlacing bracket [il, ih] and the predicted inner end `pred` (the side the value moves towards)
+      R il[kMaxBatch], ih[kMaxBatch], pred[kMaxBatch], xs[2 * kMaxBatch];
+      size_t cnt[2 * kMaxBatch];
+      bool have[kMaxBatch];
+      for (size_t k = 0; k < nb; ++k) {
+        const size_t r = r0 + k;
+        il[k] = g.lo;
+        ih[k] = g.hi;
+        have[k] = r < pv.size();
+        if (!find_max) {  // the r-th smallest moves DOWN, and stays above the (r-1)-th smallest of T_{m-1}
+          if (have[k]) ih[k] = std::min(g.hi, pv[r] + slack);
+          if (r >= 1 && r - 1 < pv.size()) il[k] = std::max(g.lo, pv[r - 1] - slack);
+        } else {  // mirrored
+          if (have[k]) il[k] = std::max(g.lo, pv[r] - slack);
+          if (r >= 1 && r - 1 < pv.size()) ih[k] = std::min(g.hi, pv[r - 1] + slack);
+        }
+        const R d = (have[k] && r < state->delta.size()) ? state->delta[r] : std::numeric_limits<R>::infinity();
+        const R step = std::max(4 * d, 64 * slack);
+        if (!find_max)
+          pred[k] = (have[k] && std::isfinite(d)) ? std::max(il[k], pv[r] - step) : il[k];
+        else
+          pred[k] = (have[k] && std::isfinite(d)) ? std::min(ih[k], pv[r] + step) : ih[k];
+        xs[2 * k] = find_max ? il[k] : pred[k];      // candidate lower end
+        xs[2 * k + 1] = find_max ? pred[k] : ih[k];  // candidate upper end
       }
-    }
-    for (size_t r = 0; r < nroot; ++r) {
-      bool ok = lo[r] < hi[r] && sturm_count(a, b, m, lo[r], g.pivmin) <= want[r] &&
-                sturm_count(a, b, m, hi[r], g.pivmin) >= want[r] + 1;
-      if (!ok) {
-        lo[r] = g.lo;
-        hi[r] = g.hi;
+      sturm_counts_batched(a, bb.data(), m, xs, 2 * nb, g.pivmin, cnt);
+      // ends that failed the check are replaced by the interlacing end (one more sweep), then by Gerschgorin
+      R ys[2 * kMaxBatch];
+      size_t cnt2[2 * kMaxBatch];
+      bool retry = false;
+      for (size_t k = 0; k < nb; ++k) {
+        const size_t w = want[r0 + k];
+        const bool lo_ok = cnt[2 * k] <= w, hi_ok = cnt[2 * k + 1] >= w + 1;
+        ys[2 * k] = lo_ok ? xs[2 * k] : il[k];
+        ys[2 * k + 1] = hi_ok ? xs[2 * k + 1] : ih[k];
+        if (!lo_ok || !hi_ok) retry = true;
+      }
+      if (retry) sturm_counts_batched(a, bb.data(), m, ys, 2 * nb, g.pivmin, cnt2);
+      for (size_t k = 0; k < nb; ++k) {
+        const size_t w = want[r0 + k];
+        const size_t cl = retry ? cnt2[2 * k] : cnt[2 * k], ch = retry ? cnt2[2 * k + 1] : cnt[2 * k + 1];
+        lo[r0 + k] = (cl <= w) ? ys[2 * k] : g.lo;
+        hi[r0 + k] = (ch >= w + 1) ? ys[2 * k + 1] : g.hi;
+        if (!(lo[r0 + k] < hi[r0 + k])) {
+          lo[r0 + k] = g.lo;
+          hi[r0 + k] = g.hi;
+        }
       }
     }
   }
 
   for (size_t r0 = 0; r0 < nroot; r0 += kMaxBatch) {
     const size_t nb = std::min(kMaxBatch, nroot - r0);
-    R l[kMaxBatch], h[kMaxBatch], x[kMaxBatch], q[kMaxBatch];
+    R l[kMaxBatch], h[kMaxBatch], x[kMaxBatch];
     size_t cnt[kMaxBatch];
     bool active[kMaxBatch];
     for (size_t r = 0; r < nb; ++r) {
@@ -146,21 +210,7 @@ inline void extreme_eigenvalues(const R* a, const R* b, size_t m, size_t nroot, 
         any = any || active[r];
       }
       if (!any) break;
-      for (size_t r = 0; r < nb; ++r) {
-        q[r] = a[0] - x[r];
-        if (std::abs(q[r]) < g.pivmin) q[r] = -g.pivmin;
-        cnt[r] = q[r] < 0 ? 1 : 0;
-      }
-      for (size_t i = 1; i < m; ++i) {
-        const R bb = b[i - 1] * b[i - 1];
-        const R ai = a[i];
-        for (size_t r = 0; r < nb; ++r) {  // independent recurrences: vectorised / pipelined divisions
-          R t = ai - x[r] - bb / q[r];
-          t = (std::abs(t) < g.pivmin) ? -g.pivmin : t;
-          q[r] = t;
-          cnt[r] += t < 0 ? 1 : 0;
-        }
-      }
+      sturm_counts_batched(a, bb.data(), m, x, nb, g.pivmin, cnt);
       for (size_t r = 0; r < nb; ++r) {
         if (!active[r]) continue;
         if (cnt[r] >= want[r0 + r] + 1)
@@ -172,6 +222,10 @@ inline void extreme_eigenvalues(const R* a, const R* b, size_t m, size_t nroot, 
     for (size_t r = 0; r < nb; ++r) out[r0 + r] = l[r] + (h[r] - l[r]) * R(0.5);
   }
   if (state) {
+    std::vector<R> d(nroot, std::numeric_limits<R>::infinity());
+    if (state->prev_m + 1 == m && state->prev_max == find_max)
+      for (size_t r = 0; r < nroot && r < state->prev.size(); ++r) d[r] = std::abs(out[r] - state->prev[r]);
+    state->delta = d;
     state->prev = out;
     state->prev_m = m;
     state->prev_max = find_max;

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "lambda_lanczos_b200/exponentiator.hpp"
+#include "lambda_lanczos_b200/functor_operator.cuh"
 #include "lambda_lanczos_b200/lambda_lanczos.hpp"
 
 namespace ll = lambda_lanczos_b200;
@@ -176,6 +177,47 @@ void DYNAMIC_MATRIX() {  // :262-308 — matrix-free user kernel, smallest eigen
   }
   EXPECT_NEAR(correct, eigvalue, std::abs(correct * engine.eps) * 4);
   for (size_t i = 0; i < n; ++i) EXPECT_NEAR(sign * v[i] / std::sqrt(nrm), eigvec[i], std::abs(correct * engine.eps * 10) * 4);
+}
+
+// The same case with the operator written as a user __device__ functor (functor_operator.cuh) — the GPU counterpart of
+// the reference's matrix-free lambda (src/samples/sample3_dynamic.cpp:17-22).
+struct HopFunctor {
+  size_t n;
+  __device__ double operator()(size_t i, const double* x) const { return -(i > 0 ? x[i - 1] : 0.0) - (i + 1 < n ? x[i + 1] : 0.0); }
+};
+struct HopFunctorComplex {
+  size_t n;
+  __device__ double2 operator()(size_t i, const double2* x) const {
+    double2 s = make_double2(0.0, 0.0);
+    if (i > 0) { s.x -= x[i - 1].x; s.y -= x[i - 1].y; }
+    if (i + 1 < n) { s.x -= x[i + 1].x; s.y -= x[i + 1].y; }
+    return s;
+  }
+};
+void DYNAMIC_MATRIX_FUNCTOR() {
+  const size_t n = 1000;
+  const double correct = -2.0 * std::cos(M_PI / (n + 1));
+  {
+    LambdaLanczos<double> engine(ll::make_functor_operator<double>(*g_ctx, n, HopFunctor{n}), n, false, 1);
+    engine.init_vector = vector_initializer<double>;
+    double eigvalue;
+    vector<double> eigvec(n);
+    engine.run(eigvalue, eigvec);
+    EXPECT_NEAR(correct, eigvalue, std::abs(correct) * 1e-10);
+    const double sign = eigvec[0] / std::abs(eigvec[0]);
+    double nrm = 0, err = 0;
+    for (size_t i = 0; i < n; ++i) nrm += std::pow(std::sin((i + 1) * M_PI / (n + 1)), 2);
+    for (size_t i = 0; i < n; ++i) err = std::max(err, std::abs(sign * std::sin((i + 1) * M_PI / (n + 1)) / std::sqrt(nrm) - eigvec[i]));
+    EXPECT_NEAR(0.0, err, 1e-7);
+  }
+  {
+    LambdaLanczos<complex<double>> engine(ll::make_functor_operator<complex<double>>(*g_ctx, n, HopFunctorComplex{n}), n, false, 1);
+    engine.init_vector = vector_initializer<complex<double>>;
+    double eigvalue;
+    vector<complex<double>> eigvec(n);
+    engine.run(eigvalue, eigvec);
+    EXPECT_NEAR(correct, eigvalue, std::abs(correct) * 1e-10);
+  }
 }
 
 void HERMITIAN_MATRIX() {  // :375-409
@@ -404,6 +446,7 @@ int main() {
     RUN(SIMPLE_MATRIX_FLOAT);
     RUN(MULTIPLE_VALUE_RETURN_FEATURE);
     RUN(DYNAMIC_MATRIX);
+    RUN(DYNAMIC_MATRIX_FUNCTOR);
     RUN(HERMITIAN_MATRIX);
     RUN(SINGLE_ELEMENT_MATRIX);
     RUN(MULTIPLE_EIGENPAIRS);
