@@ -71,44 +71,65 @@ __global__ void __launch_bounds__(kThreads) k_xxz_states(uint32_t* __restrict__ 
 // contiguous 256-byte read; on low bonds the offsets are a few hundred elements at most and hit L1.  Only the periodic
 // wrap bond (bits L-1 and 0) re-ranks through the two Lin tables.  The state itself comes from a 4-byte-per-row table
 // (A_bytes = 4 n).
-template <class T>
-__global__ void __launch_bounds__(kThreads, 4)
+template <class T, bool SHARDED>
+__global__ void __launch_bounds__(kThreads, 6)
     k_xxz_apply(const T* __restrict__ x, T* __restrict__ y, const uint32_t* __restrict__ states, XxzParams p,
                 typename Num<T>::R sigma, double* pa, PeerMsg msg) {
   using R = typename Num<T>::R;
   __shared__ double scratch[kWarps];
-  __shared__ uint32_t pascal[32][33];  // pascal[b][c] = C(b, c); the padding column spreads rows over the banks
-  for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[i >> 5][i & 31] = (uint32_t)c_binom[i >> 5][i & 31];
+  __shared__ uint32_t pascal[32 * 33];  // pascal[b*33 + c] = C(b, c); the odd stride spreads rows over the banks
+  for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
   __syncthreads();
   const uint32_t lo_mask = (1u << p.half) - 1u;
   const int nbonds = p.periodic ? p.L : p.L - 1;
   const int inner = p.L - 1;  // bonds (b, b+1) that stay inside the bit string
+  const uint32_t inner_mask = (1u << (p.L - 1)) - 1u;
+  const uint32_t top = 1u << (p.L - 1);
   const T* __restrict__ xg = reinterpret_cast<const T*>(p.x_all);
+  // every index fits 32 bits: the largest sector (L = 32, 16 up spins) has 601 080 390 states
+  const int32_t n = (int32_t)p.n, row0 = (int32_t)p.row0;
+  const int32_t stride = (int32_t)(gridDim.x * kThreads);
   double dot = 0.0;
-  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < p.n; r += (int64_t)gridDim.x * kThreads) {
+  for (int32_t r = (int32_t)(blockIdx.x * kThreads + threadIdx.x); r < n; r += stride) {
     const uint32_t s = __ldg(states + r);
-    // anti-parallel bonds: bit b set <=> sites b and b+1 differ (bit L-1 = wrap bond under periodic boundaries)
-    uint32_t d = (s ^ (s >> 1)) & ((1u << (p.L - 1)) - 1u);
+    // anti-parallel bonds: bit b set <=> sites b and b+1 differ
+    const uint32_t d = (s ^ (s >> 1)) & inner_mask;
     T acc = zero_of(T());
+    // walk the bonds with the state and the bond mask shifted down one place per step; `pi` tracks the address of
+    // pascal[b][c], c = number of set bits below b (next row: +33, one more set bit below: +1)
+    uint32_t sc = s, dc = d;
+    const uint32_t* pi = pascal;
 #pragma unroll 4
     for (int b = 0; b < inner; ++b) {
-      if ((d >> b) & 1u) {
-        const int c = __popc(s & ((1u << b) - 1u));
-        const int64_t delta = (int64_t)pascal[b][c];
-        const int64_t j = ((s >> b) & 1u) ? r + delta : r - delta;  // local index of the target (may leave the block)
-        const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + (j + p.row0));
+      const uint32_t up = sc & 1u;
+      if (dc & 1u) {
+        const int32_t delta = (int32_t)*pi;
+        const int32_t j = up ? r + delta : r - delta;  // local index of the flipped state (may leave the block)
+        T xv;
+        if (SHARDED)
+          xv = ((uint32_t)j < (uint32_t)n) ? __ldg(x + j) : __ldg(xg + (j + row0));
+        else
+          xv = __ldg(x + j);
         acc = add_t(acc, xv);
       }
+      pi += 33 + up;
+      sc >>= 1;
+      dc >>= 1;
     }
-    if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) {
-      d |= (1u << (p.L - 1));
-      const uint32_t t = s ^ ((1u << (p.L - 1)) | 1u);
-      const int64_t jg = (int64_t)__ldg(p.rank_lo + (t & lo_mask)) + (int64_t)__ldg(p.rank_hi + (t >> p.half));
-      const int64_t j = jg - p.row0;
-      const T xv = (xg == nullptr || (j >= 0 && j < p.n)) ? __ldg(x + j) : __ldg(xg + jg);
+    int anti = __popc(d);
+    if (p.periodic && (((s >> (p.L - 1)) ^ s) & 1u)) {  // wrap bond (bits L-1 and 0): re-rank through the Lin tables
+      ++anti;
+      const uint32_t t = s ^ (top | 1u);
+      const int32_t jg = (int32_t)(__ldg(p.rank_lo + (t & lo_mask)) + __ldg(p.rank_hi + (t >> p.half)));
+      const int32_t j = jg - row0;
+      T xv;
+      if (SHARDED)
+        xv = ((uint32_t)j < (uint32_t)n) ? __ldg(x + j) : __ldg(xg + jg);
+      else
+        xv = __ldg(x + j);
       acc = add_t(acc, xv);
     }
-    const R diag = (R)(p.jz4 * (double)(nbonds - 2 * __popc(d)));
+    const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
     const T xi = x[r];
     T yi = scale_real(acc, (R)p.jxy2);
     yi = add_t(yi, scale_real(xi, diag + sigma));
@@ -142,10 +163,14 @@ struct XxzOpBase : OpBase {
 
 template <class T> struct XxzOp : XxzOpBase {
   int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg* alpha_msg) override {
-    int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
+    // persistent: exactly the 6 CTAs per SM that __launch_bounds__(kThreads, 6) keeps resident
+    int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 6));
     if (g < 1) g = 1;
-    k_xxz_apply<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa,
-                                                        alpha_msg ? *alpha_msg : PeerMsg());
+    const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
+    if (prm.x_all)
+      k_xxz_apply<T, true><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg);
+    else
+      k_xxz_apply<T, false><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_apply: %s", cudaGetErrorString(e));

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--L5", type=int, default=28)
     ap.add_argument("--steps5", type=int, default=100)
     ap.add_argument("--cap", type=int, default=192, help="max_iteration for the configurations that cannot converge in HBM")
+    ap.add_argument("--cap4", type=int, default=0, help="max_iteration for config 4 (0 = to convergence; a single GPU holds ~120 vectors of L=30)")
     ap.add_argument("--cpu", action="store_true")
     args = ap.parse_args()
 
@@ -150,8 +151,8 @@ def main():
             row0, nl = wl.partition(n, rank, world)
             rs = np.random.RandomState(1 + rank)  # start vector generated per block (a 155M-entry global vector per rank is wasteful)
             start = rs.uniform(-1, 1, nl)
-            lanczos_case(f"config4 XXZ chain L={L} Sz=0 (dim {n}) matrix-free, ground state", mk, n, np.float64, False, 1, start=start,
-                         extra={"note": "start vector seeded per row block"})
+            lanczos_case(f"config4 XXZ chain L={L} Sz=0 (dim {n}) matrix-free, ground state" + (f", max_iteration={args.cap4}" if args.cap4 else ""),
+                         mk, n, np.float64, False, 1, args.cap4 or None, start=start, extra={"note": "start vector seeded per row block"})
         elif c == "c5":
             L = args.L5
             op = pkg.Operator.xxz(ctx, L, dtype=np.complex128)
