@@ -136,6 +136,12 @@ int llz_op_rows(llz_op_t op, int64_t* n_local);
 int llz_op_shape(llz_op_t op, int64_t* n_local, int64_t* n_global, int64_t* row0);
 /* Algorithmic bytes one apply has to move for the operator itself (A_bytes of SURVEY.md §8d; 0 for matrix-free). */
 int llz_op_bytes(llz_op_t op, int64_t* bytes);
+/* Gerschgorin radius max_i sum_j |a_ij| of the whole operator (group-wide for row-sharded operators): every eigenvalue
+ * lies in [-radius, radius], so eigenvalue_offset = -radius (find_maximum) or +radius (minimum) makes the wanted
+ * end of the spectrum the dominant one — the job of the reference's stand-alone helper
+ * src/determine_eigenvalue_offset/determine_eigenvalue_offset.cpp:12-49, on the device.  CSR / SELL: exact;
+ * XXZ: the analytic bound; user callbacks: LLZ_ERR_UNSUPPORTED. */
+int llz_op_gerschgorin_radius(llz_op_t op, double* radius);
 /* y = A x on device vectors (stand-alone use and Exponentiator::taylor_run, exponentiator.hpp:191). */
 int llz_op_apply(llz_op_t op, llz_vec_t x, llz_vec_t y);
 

@@ -201,6 +201,12 @@ class Operator:
         _check(lib().llz_op_bytes(self.h, C.byref(b)), "llz_op_bytes")
         return int(b.value)
 
+    def gerschgorin_radius(self) -> float:
+        """max_i sum_j |a_ij| (every eigenvalue lies in [-radius, radius]): the value to choose eigenvalue_offset from."""
+        r = C.c_double(0)
+        _check(lib().llz_op_gerschgorin_radius(self.h, C.byref(r)), "llz_op_gerschgorin_radius")
+        return float(r.value)
+
     def apply(self, x: "Vector", y: "Vector"):
         _check(lib().llz_op_apply(self.h, x.h, y.h), "llz_op_apply")
 

@@ -135,6 +135,12 @@ __device__ __forceinline__ double re_conj_mul(double a, double b) { return a * b
 __device__ __forceinline__ double re_conj_mul(float2 a, float2 b) { return (double)a.x * b.x + (double)a.y * b.y; }
 __device__ __forceinline__ double re_conj_mul(double2 a, double2 b) { return a.x * b.x + a.y * b.y; }
 
+// |v| as the reference's row-sum tool takes it (std::abs, also for complex entries)
+__device__ __forceinline__ double abs1(float v) { return fabs((double)v); }
+__device__ __forceinline__ double abs1(double v) { return fabs(v); }
+__device__ __forceinline__ double abs1(float2 v) { return hypot((double)v.x, (double)v.y); }
+__device__ __forceinline__ double abs1(double2 v) { return hypot(v.x, v.y); }
+
 // component access (for reductions that treat an accumulator as NC reals)
 __device__ __forceinline__ float comp(float v, int) { return v; }
 __device__ __forceinline__ double comp(double v, int) { return v; }

@@ -113,6 +113,12 @@ struct OpBase {
     (void)x;
     return LLZ_OK;
   }
+  // max_i sum_j |a_ij| over the LOCAL rows (Gerschgorin radius); LLZ_ERR_UNSUPPORTED for operators without stored
+  // or analytically known entries (user callbacks).
+  virtual int abs_row_sum_max(double* out) {
+    (void)out;
+    return fail(LLZ_ERR_UNSUPPORTED, "this operator kind cannot report its row sums");
+  }
   // y = A x + sigma x ; per-CTA partials of Re<x,y> into alpha_partials[0..*n_partials) (device), all on ctx->stream.
   // Returns LLZ_OK or an error.  Implementations that cannot fuse the dot leave *n_partials = 0 and the engine runs
   // a separate dot kernel.

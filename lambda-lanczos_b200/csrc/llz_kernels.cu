@@ -222,9 +222,10 @@ __global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
   }
   if (a.msg.ch.G > 0 && a.publish) {
     __shared__ int is_last;
-    if (ty == 0) __threadfence_system();  // the storing threads: their NVLink stores are performed before the ticket
-    __syncthreads();
+    __syncthreads();  // the CTA's NVLink stores happen-before thread 0's fence (bar.sync), which makes them — being
+                      // cumulative — visible system-wide before the ticket is taken
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned int t = atomicAdd(a.ticket, 1u);
       is_last = (t == gridDim.x - 1);
       if (is_last) *a.ticket = 0;

@@ -53,9 +53,9 @@ __global__ void __launch_bounds__(kThreads) k_halo_push(const T* __restrict__ x,
     while (i >= hp.start[q + 1]) ++q;
     reinterpret_cast<T*>(hp.dst[q])[i - hp.start[q]] = __ldg(x + idx[i]);
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative: covers the stores of the whole CTA ordered before it by the barrier
     const unsigned int t = atomicAdd(msg.ticket, 1u);
     last_cta = (t == gridDim.x - 1);
     if (last_cta) *msg.ticket = 0;
@@ -288,6 +288,45 @@ __global__ void __launch_bounds__(kThreads, 3)
   finish_scalar(t, pa, msg, scratch);
 }
 
+// Gerschgorin radius: per-CTA maximum of the absolute row sums (CSR: one thread per row; SELL: one lane per row).
+template <class T, class IDX>
+__global__ void __launch_bounds__(kThreads) k_csr_rowsum_max(const IDX* __restrict__ rowptr, const T* __restrict__ vals, int64_t n, double* out) {
+  __shared__ double red[kThreads];
+  double m = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    double s = 0.0;
+    for (IDX p = rowptr[r]; p < rowptr[r + 1]; ++p) s += abs1(vals[p]);
+    m = fmax(m, s);
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_sell_rowsum_max(const int64_t* __restrict__ slice_ptr, const T* __restrict__ sval, int64_t n_slices, double* out) {
+  __shared__ double red[kThreads];
+  const int lane = threadIdx.x & 31;
+  double m = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); s < n_slices; s += (int64_t)gridDim.x * kWarps) {
+    const int64_t p0 = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - p0) / kSellC);
+    double t = 0.0;
+    for (int j = 0; j < w; ++j) t += abs1(sval[p0 + (int64_t)j * kSellC + lane]);  // padding holds zeros
+    m = fmax(m, t);
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
 template <class T> struct CsrOp : OpBase {
   int64_t n_cols = 0;
   int64_t nnz = 0;
@@ -511,6 +550,23 @@ template <class T> struct CsrOp : OpBase {
     sell = true;
     ctx->launches += 3;
     bytes = padded_nnz * (int64_t)(sizeof(T) + 4) + (n_slices + 1) * 8 + (d_perm ? n * 4 : 0);
+    return LLZ_OK;
+  }
+
+  int abs_row_sum_max(double* out) override {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_local + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 4));
+    double* d = ctx->d_partials;  // kMaxGrid * 2 doubles
+    if (sell)
+      k_sell_rowsum_max<T><<<grid, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_sval, n_slices, d);
+    else if (idx32)
+      k_csr_rowsum_max<T, int32_t><<<grid, kThreads, 0, ctx->stream>>>((const int32_t*)d_rowptr, d_vals, n_local, d);
+    else
+      k_csr_rowsum_max<T, int64_t><<<grid, kThreads, 0, ctx->stream>>>((const int64_t*)d_rowptr, d_vals, n_local, d);
+    std::vector<double> h((size_t)grid);
+    LLZ_CUDA(cudaMemcpyAsync(h.data(), d, sizeof(double) * (size_t)grid, cudaMemcpyDeviceToHost, ctx->stream));
+    LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->launches++;
+    *out = *std::max_element(h.begin(), h.end());
     return LLZ_OK;
   }
 
@@ -856,6 +912,17 @@ int llz_op_shape(llz_op_t op, int64_t* n_local, int64_t* n_global, int64_t* row0
   if (n_local) *n_local = op->impl->n_local;
   if (n_global) *n_global = op->impl->n_global;
   if (row0) *row0 = op->impl->row0;
+  return LLZ_OK;
+}
+
+int llz_op_gerschgorin_radius(llz_op_t op, double* radius) {
+  if (!op || !op->impl || !radius) return fail(LLZ_ERR_INVALID, "null");
+  OpBase* o = op->impl;
+  double local = 0.0;
+  LLZ_TRY(o->abs_row_sum_max(&local));
+  std::vector<double> all((size_t)o->ctx->nranks, local);
+  LLZ_TRY(comm_allgather_host(o->ctx, &local, all.data(), sizeof(double)));
+  *radius = *std::max_element(all.begin(), all.end());
   return LLZ_OK;
 }
 

@@ -7,6 +7,7 @@
 // consecutive states once and steps to the next ones with Gosper's bit trick.
 // The alpha = Re<x, Hx> dot is fused into the epilogue like the CSR kernel's.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "llz_device.cuh"
@@ -152,6 +153,12 @@ struct XxzOpBase : OpBase {
     if (d_hi) dev_free(ctx, d_hi);
     if (d_xall) dev_free(ctx, d_xall);
     if (d_states) dev_free(ctx, d_states);
+  }
+  // every row has at most `nbonds` off-diagonal entries Jxy/2 and a diagonal of magnitude <= nbonds |Jz|/4
+  int abs_row_sum_max(double* out) override {
+    const int nbonds = prm.periodic ? prm.L : prm.L - 1;
+    *out = nbonds * (fabs(prm.jz4) + fabs(prm.jxy2));
+    return LLZ_OK;
   }
   // Row-sharded: every rank sends its block of x to every peer (bit flips on high sites land anywhere in the sector).
   int prepare(const void* x) override {

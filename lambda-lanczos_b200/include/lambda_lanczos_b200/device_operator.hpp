@@ -98,6 +98,13 @@ class DeviceOperator {
     check(llz_op_bytes(h_.get(), &b), "llz_op_bytes");
     return b;
   }
+  // max_i sum_j |a_ij|: all eigenvalues lie in [-r, r] — what to choose eigenvalue_offset from (the reference ships a
+  // stand-alone tool for this, src/determine_eigenvalue_offset/determine_eigenvalue_offset.cpp)
+  double gerschgorin_radius() const {
+    double r = 0.0;
+    check(llz_op_gerschgorin_radius(h_.get(), &r), "llz_op_gerschgorin_radius");
+    return r;
+  }
   // y = A x on device vectors
   void operator()(const DeviceVector<T>& x, DeviceVector<T>& y) const { check(llz_op_apply(h_.get(), x.get(), y.get()), "llz_op_apply"); }
 

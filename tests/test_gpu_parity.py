@@ -143,6 +143,26 @@ def test_sell_operator_is_bit_identical_to_csr(pkg, ctx, wl, dtype, sigma):
     assert np.all(np.isfinite(y[~touched]))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_gerschgorin_radius_matches_numpy(pkg, ctx, wl, dtype):
+    """max abs row sum on the device (determine_eigenvalue_offset.cpp:12-29 of the reference) for CSR and SELL storage;
+    used as eigenvalue_offset it turns the smallest eigenvalue into the dominant one."""
+    for csr in (ragged_csr(3001, 1, dtype), wl.laplacian2d_csr(37, 41, dtype=dtype)):
+        expect = np.abs(wl_dense_rowsum(csr))
+        for make in (pkg.Operator.csr, pkg.Operator.sell):
+            got = make(ctx, *csr).gerschgorin_radius()
+            assert abs(got - expect) <= (1e-5 if np.dtype(dtype) == np.float32 else 1e-12) * expect
+    op = pkg.Operator.xxz(ctx, 12)
+    dense = np.abs(wl_dense_rowsum(wl.xxz_csr(12)))
+    assert op.gerschgorin_radius() >= dense - 1e-12
+
+
+def wl_dense_rowsum(csr):
+    rowptr, colidx, vals = csr
+    sums = np.add.reduceat(np.abs(vals.astype(np.complex128)), rowptr[:-1][np.diff(rowptr) > 0]) if vals.size else np.zeros(1)
+    return float(sums.max())
+
+
 def test_sell_rejects_bad_sigma(pkg, ctx, wl):
     with pytest.raises(pkg.LlzError) as e:
         pkg.Operator.sell(ctx, *wl.laplacian2d_csr(8), sigma=48)
