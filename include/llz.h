@@ -94,7 +94,8 @@ int llz_ctx_rank(llz_ctx_t ctx, int* rank, int* nranks);
  * through CUDA-IPC mapped peer memory written from inside the producing kernels (csrc/llz_peer.cuh), 0 when it uses
  * NCCL all-reduces (single rank, IPC unavailable, or LLZ_P2P=0 in the environment). */
 int llz_ctx_peer_channels(llz_ctx_t ctx, int* enabled);
-/* The row partition every built-in operator and the bench use: rank r owns [n*r/G, n*(r+1)/G).  Pure host arithmetic. */
+/* The row partition every built-in operator and the bench use: rank r owns [b(r), b(r+1)) with b(r) = floor(n*r/G)
+ * rounded down to a multiple of 4 (b(0) = 0, b(G) = n), so row blocks start 16-byte aligned.  Pure host arithmetic. */
 int llz_partition(int64_t n_global, int rank, int nranks, int64_t* row0, int64_t* n_local);
 /* Host-side halo planning for the local row block of a CSR matrix with GLOBAL column indices (no GPU involved):
  * boundaries[0..nranks] are the row-block boundaries of the group.  Outputs (each may be NULL): the column indices in

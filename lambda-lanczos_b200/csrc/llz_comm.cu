@@ -67,8 +67,9 @@ struct Comm {
   // peer-memory channels for the per-iteration scalar reductions (llz_peer.cuh); G == 0 when unavailable
   void* p2p_local = nullptr;
   void* p2p_peer[kMaxRanks] = {};
-  PeerChannel ch[4];
-  unsigned long long seq[4] = {0, 0, 0, 0};
+  PeerChannel ch[5];
+  unsigned long long seq[5] = {0, 0, 0, 0, 0};
+  std::vector<ExchangeBuffer*> xbufs;  // IPC-mapped whole-vector buffers (fused all-gather), kept until the context dies
   unsigned int* ticket = nullptr;
   // halo window: part of the same IPC-mapped allocation, sub-allocated by row-sharded operators for the entries of x
   // their peers push to them (first-fit free list of [offset, bytes), offsets relative to the window)
@@ -163,7 +164,7 @@ static int p2p_setup(llz_ctx_t ctx) {
   int want = !(env && env[0] == '0');
   size_t win_bytes = (size_t)256 << 20;
   if (const char* w = getenv("LLZ_HALO_WINDOW_MB")) win_bytes = (size_t)std::max(0L, atol(w)) << 20;
-  const size_t chan_bytes = (channel_bytes(G, kScalarPayload) * 3 + channel_bytes(G, kCoefPayload) + 256 + 255) / 256 * 256;
+  const size_t chan_bytes = (channel_bytes(G, kScalarPayload) * 4 + channel_bytes(G, kCoefPayload) + 256 + 255) / 256 * 256;
   const size_t bytes = chan_bytes + win_bytes;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
@@ -211,12 +212,12 @@ static int p2p_setup(llz_ctx_t ctx) {
     cudaGetLastError();
     return LLZ_OK;  // NCCL path
   }
-  const int payload[4] = {kScalarPayload, kScalarPayload, kCoefPayload, kScalarPayload};
+  const int payload[5] = {kScalarPayload, kScalarPayload, kCoefPayload, kScalarPayload, kScalarPayload};
   size_t off = 256;  // first 256 bytes: status word (+0) and the last-CTA ticket (+64)
   c->win_off = chan_bytes;
   c->win_bytes = win_bytes;
   c->win_free.assign(1, std::make_pair((size_t)0, win_bytes));
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) {
     PeerChannel& ch = c->ch[k];
     ch.G = G;
     ch.rank = ctx->rank;
@@ -271,6 +272,56 @@ void* comm_window_ptr(llz_ctx_t ctx, int r, int64_t off) {
   return static_cast<char*>(c->p2p_peer[r]) + c->win_off + off;
 }
 
+// A buffer of `bytes` on every rank, each mapped into every peer (CUDA IPC) — where producers store the vector they
+// write so that the next operator apply finds the whole input vector without an all-gather.  Collective (all ranks
+// call it in the same order); buffers are recycled by size and only freed with the context, so that releasing one is
+// a local operation.  nullptr when the group has no peer channels or any rank failed to allocate / map.
+ExchangeBuffer* comm_exchange_buffer_acquire(llz_ctx_t ctx, size_t bytes) {
+  if (!comm_p2p(ctx) || bytes == 0) return nullptr;
+  Comm* c = ctx->comm;
+  for (ExchangeBuffer* b : c->xbufs)
+    if (!b->in_use && b->bytes == bytes) {
+      b->in_use = true;
+      return b;
+    }
+  const int G = ctx->nranks;
+  ExchangeBuffer* b = new ExchangeBuffer();
+  b->bytes = bytes;
+  struct Rec {
+    cudaIpcMemHandle_t h;
+    int ok;
+    int pad;
+  } rec;
+  memset(&rec, 0, sizeof(rec));
+  rec.ok = dev_malloc(ctx, &b->local, bytes) == cudaSuccess;
+  if (rec.ok && cudaIpcGetMemHandle(&rec.h, b->local) != cudaSuccess) rec.ok = 0;
+  cudaGetLastError();
+  std::vector<Rec> all((size_t)G);
+  int ok = comm_allgather_host(ctx, &rec, all.data(), sizeof(Rec)) == LLZ_OK;
+  for (int r = 0; r < G && ok; ++r) ok = all[(size_t)r].ok;
+  for (int r = 0; r < G && ok; ++r) {
+    if (r == ctx->rank) {
+      b->peer[r] = b->local;
+    } else if (cudaIpcOpenMemHandle(&b->peer[r], all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      b->peer[r] = nullptr;
+      ok = 0;
+    }
+  }
+  int mapped = ok;
+  std::vector<int> mapped_all((size_t)G, 0);
+  if (comm_allgather_host(ctx, &mapped, mapped_all.data(), sizeof(int)) != LLZ_OK) ok = 0;
+  for (int r = 0; r < G; ++r) ok = ok && mapped_all[(size_t)r];
+  b->in_use = ok;
+  b->usable = ok;
+  c->xbufs.push_back(b);  // kept even when unusable: its memory and mappings are released with the context
+  return ok ? b : nullptr;
+}
+void comm_exchange_buffer_release(llz_ctx_t ctx, ExchangeBuffer* b) {
+  (void)ctx;
+  if (b) b->in_use = false;
+}
+
 // The NEXT message of a channel (every rank calls this in the same order); an unused message (ch.G == 0) when the
 // group has no peer channels.
 PeerMsg comm_next_message(llz_ctx_t ctx, int which) {
@@ -297,11 +348,19 @@ void comm_destroy(llz_ctx_t ctx) {
     Comm* c = ctx->comm;
     for (int r = 0; r < ctx->nranks; ++r)
       if (r != ctx->rank && c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+    for (ExchangeBuffer* b : c->xbufs)
+      for (int r = 0; r < ctx->nranks; ++r)
+        if (r != ctx->rank && b->peer[r]) cudaIpcCloseMemHandle(b->peer[r]);
     // every rank must have unmapped this rank's inbox before it is freed: one blocking collective
     double* d = ctx->d_result;
     if (d && nccl().AllReduce(d, d, 1, ncclDouble, ncclSum, c->nccl, ctx->stream) == ncclSuccess) cudaStreamSynchronize(ctx->stream);
     cudaFree(c->p2p_local);
     c->p2p_local = nullptr;
+    for (ExchangeBuffer* b : c->xbufs) {
+      if (b->local) dev_free(ctx, b->local);
+      delete b;
+    }
+    c->xbufs.clear();
     cudaGetLastError();
   }
   if (ctx->comm) {

@@ -235,12 +235,20 @@ __device__ __forceinline__ double block_sum_partials(const double* __restrict__ 
 // stores the CTA's partial; row-sharded with peer channels, the LAST CTA to finish (ticket) also sums the partials and
 // delivers the rank's value to every GPU's inbox — thread p stores to rank p, fences and announces — so no separate
 // reduction kernel or collective sits between the producer and the consumer.  Call with all threads of the CTA.
-__device__ __forceinline__ void finish_scalar(double cta_value, double* partials, const PeerMsg& msg, double* scratch) {
+// `push` (optional): the kernel also stored its output vector into the peers' exchange buffers (fused all-gather);
+// the last CTA announces that message too.  (The callers' block_sum barrier orders every thread's stores before thread
+// 0's fence, which is cumulative.)
+__device__ __forceinline__ void finish_scalar(double cta_value, double* partials, const PeerMsg& msg, double* scratch,
+                                              const GatherPush* push = nullptr) {
   if (threadIdx.x == 0) partials[blockIdx.x] = cta_value;
   if (msg.ch.G == 0) return;
   __shared__ int last_cta;
+  const bool pushing = push != nullptr && push->G > 0;
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (pushing)
+      __threadfence_system();
+    else
+      __threadfence();
     const unsigned int t = atomicAdd(msg.ticket, 1u);
     last_cta = (t == gridDim.x - 1);
     if (last_cta) *msg.ticket = 0;
@@ -255,7 +263,20 @@ __device__ __forceinline__ void finish_scalar(double cta_value, double* partials
     peer_slot(msg.ch, threadIdx.x, msg.seq, msg.ch.rank)[0] = v;
     __threadfence_system();
     peer_announce(msg.ch, threadIdx.x, msg.seq);
+  } else if (pushing && (int)threadIdx.x >= 32 && (int)threadIdx.x - 32 < push->msg.ch.G) {  // a second warp, concurrently
+    __threadfence_system();
+    peer_announce(push->msg.ch, threadIdx.x - 32, push->msg.seq);
   }
+}
+
+// Store a 128-bit packet of the vector a kernel writes into every peer's exchange buffer as well (fused all-gather).
+template <class T> __device__ __forceinline__ void push_pack(const GatherPush& push, int64_t idx, const Pack<T>& v) {
+  for (int p = 0; p < push.G; ++p)
+    if (p != push.rank) st_pack(reinterpret_cast<T*>(push.dst[p]) + idx, v);
+}
+template <class T> __device__ __forceinline__ void push_guard(const GatherPush& push, int64_t idx, int64_t n, const Pack<T>& v) {
+  for (int p = 0; p < push.G; ++p)
+    if (p != push.rank) st_guard(reinterpret_cast<T*>(push.dst[p]), idx, n, v);
 }
 
 // Transposed warp reduction: each lane holds M partial sums (M a power of two <= 32); afterwards the total of value

@@ -1,6 +1,7 @@
 // llz_halo.cpp — host-side planning for row-sharded operators (no CUDA in this file; tested on CPU).
 //
-//   llz_partition   contiguous, balanced row blocks: rank r owns [n*r/G, n*(r+1)/G)
+//   llz_partition   contiguous, balanced row blocks: rank r owns [b(r), b(r+1)), b(r) = floor(n*r/G) rounded down to a
+//                   multiple of 4 (b(0) = 0, b(G) = n)
 //   llz_halo_plan   for the local row block of a CSR matrix with GLOBAL column indices: which remote entries of x the
 //                   block references (sorted, hence grouped by owner), and the column indices rewritten to the local
 //                   "extended" numbering  [0, n_rows) = own block,  n_rows + h = h-th halo entry.
@@ -21,8 +22,15 @@ int llz_partition(int64_t n_global, int rank, int nranks, int64_t* row0, int64_t
   if (n_global < 0 || nranks < 1 || rank < 0 || rank >= nranks || !row0 || !n_local)
     return fail(LLZ_ERR_INVALID, "partition: bad argument (n=%lld, rank %d of %d)", (long long)n_global, rank, nranks);
   // 128-bit products are not needed: n < 2^40 and nranks <= 2^10 in any realistic run
-  const int64_t a = (int64_t)((__int128)n_global * rank / nranks);
-  const int64_t b = (int64_t)((__int128)n_global * (rank + 1) / nranks);
+  // interior boundaries are rounded down to a multiple of 4 elements, so that a row block starts 16-byte aligned inside
+  // a gathered vector for every element type (the fused all-gather stores 128-bit packets into the peers' buffers)
+  auto bound = [&](int r) -> int64_t {
+    if (r <= 0) return 0;
+    if (r >= nranks) return n_global;
+    return (int64_t)((__int128)n_global * r / nranks) & ~(int64_t)3;
+  };
+  const int64_t a = bound(rank);
+  const int64_t b = bound(rank + 1);
   *row0 = a;
   *n_local = b - a;
   return LLZ_OK;

@@ -43,6 +43,7 @@ inline int dtype_nc(int dtype) { return (dtype == LLZ_C64 || dtype == LLZ_C128) 
 struct Comm;         // inter-GPU plumbing (llz_comm.cu)
 struct PeerChannel;  // peer-memory message channel (llz_peer.cuh)
 struct PeerMsg;
+struct GatherPush;
 
 // Per-kernel device-time accounting (CUDA events on the context's stream), keyed by a short kernel-family name.
 struct ProfEntry {
@@ -113,6 +114,19 @@ struct OpBase {
     (void)x;
     return LLZ_OK;
   }
+  // Fused all-gather (row-sharded operators that read the WHOLE input vector): instead of gathering x before the
+  // apply, the kernel that produces the vector (update / recurrence of the previous iteration) also stores its block
+  // into every peer's exchange buffer.  plan_push() hands the producer the destinations and the message to announce
+  // (false: not supported, gather in prepare()); use_pushed() tells the operator that its next apply finds the input
+  // in the pushed buffers, still un-normalised: remote entries are multiplied by 1 / *scale on the fly.
+  virtual bool plan_push(GatherPush* push) {
+    (void)push;
+    return false;
+  }
+  virtual void use_pushed(const GatherPush& push, const double* scale) {
+    (void)push;
+    (void)scale;
+  }
   // max_i sum_j |a_ij| over the LOCAL rows (Gerschgorin radius); LLZ_ERR_UNSUPPORTED for operators without stored
   // or analytically known entries (user callbacks).
   virtual int abs_row_sum_max(double* out) {
@@ -142,6 +156,15 @@ bool comm_p2p(llz_ctx_t ctx);
 int comm_coef_capacity(llz_ctx_t ctx);
 unsigned int* comm_ticket(llz_ctx_t ctx);
 int comm_check_peers(llz_ctx_t ctx);
+// Whole-vector exchange buffers for the fused all-gather (llz_comm.cu)
+struct ExchangeBuffer {
+  size_t bytes = 0;
+  void* local = nullptr;
+  void* peer[16] = {};  // address of every rank's buffer, valid on this GPU (peer[rank] == local)
+  bool in_use = false, usable = false;
+};
+ExchangeBuffer* comm_exchange_buffer_acquire(llz_ctx_t ctx, size_t bytes);
+void comm_exchange_buffer_release(llz_ctx_t ctx, ExchangeBuffer* b);
 int64_t comm_window_alloc(llz_ctx_t ctx, size_t bytes);
 void comm_window_free(llz_ctx_t ctx, int64_t off, size_t bytes);
 void* comm_window_ptr(llz_ctx_t ctx, int rank, int64_t off);

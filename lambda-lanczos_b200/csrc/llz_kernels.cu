@@ -277,6 +277,7 @@ struct UpdateArgs {
   int cu1, cu2;
   PeerMsg coef_msg;  // row-sharded: coefficients = sum over ranks of this message (element col*NC + c)
   PeerMsg norm_msg;  // row-sharded: deliver sum(pb) group-wide from the last CTA
+  GatherPush push;   // row-sharded: also store `out` into the peers' exchange buffers (fused all-gather)
 };
 
 template <class T, int VPT, bool FULL>
@@ -359,6 +360,12 @@ __device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base,
       st_pack(out + idx, acc[i]);
     else
       st_guard(out, idx, a.n, acc[i]);
+    if (a.push.G > 0) {
+      if (FULL)
+        push_pack<T>(a.push, idx, acc[i]);
+      else
+        push_guard<T>(a.push, idx, a.n, acc[i]);
+    }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) nrm += abs2(acc[i].e[e]);  // guarded lanes hold zeros
   }
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
   }
   if (a.pb) {
     const double t = block_sum(nrm, scratch);
-    finish_scalar(t, a.pb, a.norm_msg, scratch);
+    finish_scalar(t, a.pb, a.norm_msg, scratch, &a.push);
   }
 }
 
@@ -478,6 +485,7 @@ struct RecurrenceArgs {
   double* pb;
   PeerMsg alpha_msg;
   PeerMsg norm_msg;
+  GatherPush push;
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
@@ -522,12 +530,18 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(R
       st_pack(out + idx, acc);
     else
       st_guard(out, idx, a.n, acc);
+    if (a.push.G > 0) {
+      if (full)
+        push_pack<T>(a.push, idx, acc);
+      else
+        push_guard<T>(a.push, idx, a.n, acc);
+    }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) nrm += abs2(acc.e[e]);
   }
   if (a.pb) {
     const double t = block_sum(nrm, scratch);
-    finish_scalar(t, a.pb, a.norm_msg, scratch);
+    finish_scalar(t, a.pb, a.norm_msg, scratch, &a.push);
   }
 }
 
@@ -867,6 +881,7 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
   a.coef = coef;
   a.coef_msg = coef_msg;
   a.norm_msg = norm_partials ? norm_msg : PeerMsg();
+  a.push = (norm_partials && a.norm_msg.ch.G > 0) ? fold.push : GatherPush();
   a.pb = norm_partials;
   a.fold = fold.mode;
   a.alpha = fold.alpha_out;
@@ -916,6 +931,7 @@ int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, c
   a.alpha_out = fold.alpha_out;
   a.alpha_msg = fold.alpha_msg;
   a.norm_msg = norm_partials ? fold.norm_msg : PeerMsg();
+  a.push = (norm_partials && a.norm_msg.ch.G > 0) ? fold.push : GatherPush();
   a.pb = norm_partials;
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;

@@ -92,6 +92,12 @@ struct llz_krylov_s {
   const void** d_qptrs = nullptr;
   int q_cap = 0;
   int nq = 0;
+  // fused all-gather: the vector of column `pushed_col` was also stored into the peers' exchange buffers by the
+  // kernel that produced it, for operator `pushed_op`
+  bool pushed_valid = false;
+  int64_t pushed_col = -1;
+  OpBase* pushed_op = nullptr;
+  GatherPush pushed;
   // state
   int64_t k = 0;
 
@@ -213,6 +219,7 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
     const bool last = c0 + cols >= generic;
     Fold f = (c0 == 0) ? fold : Fold();
     f.norm_msg = fold.norm_msg;
+    f.push = fold.push;  // (launch_update only honours it in the chunk that writes the final vector and its norm)
     ProfScope ps(ctx, "update", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + f.mode + 2));
     LLZ_TRY(launch_update(ctx, kry->dtype, cs, c0, cols, w, w, kry->n, kry->d_coef, f,
                           (last && want_norm) ? kry->d_pb : nullptr, norm_grid, coef_msg, fold.norm_msg));
@@ -235,6 +242,7 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
     if (c->dtype == dtype && c->n == n && c->requested_cols == max_cols) {  // revive: mapped basis memory is kept
       c->k = 0;
       c->nq = 0;
+      c->pushed_valid = false;
       c->h_flag[0] = 0;
       *out = c;
       return LLZ_OK;
@@ -413,6 +421,7 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   LLZ_CUDA(cudaSetDevice(ctx->device));
   LLZ_CUDA(cudaStreamSynchronize(ctx->stream));  // nothing of a previous run may still publish scalars
   kry->k = 0;
+  kry->pushed_valid = false;
   kry->h_flag[0] = 0;
   const size_t bytes = (size_t)kry->n * dtype_size(kry->dtype);
   void* u0 = kry->col(0);
@@ -456,7 +465,14 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
   void* y = kry->col(k);
 
   int npa = 0;
-  LLZ_TRY(op->impl->prepare(x));
+  if (kry->pushed_valid && kry->pushed_op == op->impl && kry->pushed_col == k - 1) {
+    // the previous iteration's update / recurrence kernel already delivered x to every GPU (un-normalised: the
+    // consumer divides the remote entries by beta_{k-2}, as k_scale_norm did with the local block)
+    op->impl->use_pushed(kry->pushed, kry->d_beta + (k - 2));
+  } else {
+    LLZ_TRY(op->impl->prepare(x));
+  }
+  kry->pushed_valid = false;
   Fold fold;
   fold.alpha_msg = comm_next_message(ctx, kChanAlpha);  // delivered by the last CTA of the kernel that computes <x, Ax>
   {
@@ -477,6 +493,12 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
   int grid = 0;
   ScalarSink sink;
   sink.beta_msg = comm_next_message(ctx, kChanBeta);  // delivered by the kernel that writes the norm partials
+  if (sink.beta_msg.ch.G > 0 && op->impl->plan_push(&fold.push)) {  // ... which also pushes u_k to the peers
+    kry->pushed_valid = true;
+    kry->pushed_col = k;
+    kry->pushed_op = op->impl;
+    kry->pushed = fold.push;
+  }
   if (orth == LLZ_ORTH_RECURRENCE) {
     fold.norm_msg = sink.beta_msg;
     ProfScope ps(ctx, "recurrence", (double)kry->n * (double)dtype_size(kry->dtype) * (2 + fold.mode));
@@ -494,6 +516,7 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     if (orth == LLZ_ORTH_FULL_TWICE) {
       Fold nofold;
       nofold.norm_msg = sink.beta_msg;
+      nofold.push = fold.push;
       LLZ_TRY(cgs_pass(kry, cs, y, nofold, true, &grid));
     }
   }
@@ -567,6 +590,7 @@ int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink) {
   LLZ_CUDA(cudaMemcpyAsync(kry->d_beta + (k - 1), kry->h_beta + (k - 1), sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
   kry->k = k;  // iterations enqueued beyond k used the un-refined vector: drop them
+  kry->pushed_valid = false;  // ... and so did the copy of it the peers were sent
   kry->h_flag[0] = k;
   if (shrink) *shrink = nu;
   return LLZ_OK;

@@ -8,7 +8,7 @@ namespace llz {
 // The NEXT message of a peer channel (llz_comm.cu; every rank calls this in the same order); unused (ch.G == 0) when
 // the context has no peer channels.
 PeerMsg comm_next_message(llz_ctx_t ctx, int which);
-enum { kChanAlpha = 0, kChanBeta = 1, kChanCoef = 2, kChanHalo = 3 };
+enum { kChanAlpha = 0, kChanBeta = 1, kChanCoef = 2, kChanHalo = 3, kChanGather = 4 };
 
 
 // The set of orthonormal columns a vector is projected on: `nq` separately allocated vectors (device pointer table)
@@ -33,6 +33,8 @@ struct Fold {
   PeerMsg alpha_msg;                    // row-sharded: alpha = sum over ranks of this message instead of the partials
   PeerMsg norm_msg;                     // row-sharded: the kernel that produces the norm partials (update / recurrence)
                                         // also delivers their sum as this message (consumed by scale_by_norm)
+  GatherPush push;                      // row-sharded: ... and stores the vector it writes into the peers' exchange
+                                        // buffers (fused all-gather for operators that read the whole input vector)
 };
 
 // Where scale_by_norm publishes the iteration's scalars.

@@ -39,6 +39,15 @@ struct PeerMsg {
   unsigned int* ticket = nullptr;  // device counter for last-CTA detection in the producing kernel
 };
 
+// Fused all-gather: where the producer of a vector additionally stores its row block (one destination per peer,
+// already offset to this rank's rows inside the peer's exchange buffer) and the message that announces it.
+struct GatherPush {
+  int G = 0;  // 0 => no push
+  int rank = 0;
+  void* dst[kMaxRanks] = {};
+  PeerMsg msg;
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ double* peer_slot(const PeerChannel& ch, int owner, unsigned long long seq, int src) {
   return ch.inbox[owner] + ((size_t)(seq & 1ull) * ch.G + src) * ch.payload;

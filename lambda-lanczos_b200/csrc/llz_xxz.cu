@@ -8,6 +8,7 @@
 // The alpha = Re<x, Hx> dot is fused into the epilogue like the CSR kernel's.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "llz_device.cuh"
@@ -27,6 +28,8 @@ struct XxzParams {
   int64_t row0;        // first local row (row-sharded runs)
   const void* x_all;   // row-sharded runs: the whole input vector, gathered before the launch (entries of the local
                        // block are read from x itself); null for a single rank
+  const double* x_scale;  // fused all-gather: the remote entries in x_all are still un-normalised, multiply them by
+                          // 1 / *x_scale (the norm the producer's successor kernel divided the local block by)
 };
 
 __device__ __forceinline__ uint32_t xxz_unrank(int64_t idx, int L, int n_up) {
@@ -75,10 +78,14 @@ __global__ void __launch_bounds__(kThreads) k_xxz_states(uint32_t* __restrict__ 
 template <class T, bool SHARDED>
 __global__ void __launch_bounds__(kThreads, 6)
     k_xxz_apply(const T* __restrict__ x, T* __restrict__ y, const uint32_t* __restrict__ states, XxzParams p,
-                typename Num<T>::R sigma, double* pa, PeerMsg msg) {
+                typename Num<T>::R sigma, double* pa, PeerMsg msg, PeerMsg gather_msg) {
   using R = typename Num<T>::R;
   __shared__ double scratch[kWarps];
-  __shared__ uint32_t pascal[32 * 33];  // pascal[b*33 + c] = C(b, c); the odd stride spreads rows over the banks
+  __shared__ uint32_t pascal[32 * 33];
+  if (SHARDED && gather_msg.ch.G > 0) peer_wait(gather_msg.ch, gather_msg.seq);  // the peers' blocks have landed in x_all
+  R inv = (R)1;
+  const bool rescale = SHARDED && p.x_scale != nullptr;
+  if (rescale) inv = (R)1 / (R)(*p.x_scale);  // exactly the factor k_scale_norm applied to the owner's copy  // pascal[b*33 + c] = C(b, c); the odd stride spreads rows over the banks
   for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
   __syncthreads();
   const uint32_t lo_mask = (1u << p.half) - 1u;
@@ -107,10 +114,16 @@ __global__ void __launch_bounds__(kThreads, 6)
         const int32_t delta = (int32_t)*pi;
         const int32_t j = up ? r + delta : r - delta;  // local index of the flipped state (may leave the block)
         T xv;
-        if (SHARDED)
-          xv = ((uint32_t)j < (uint32_t)n) ? __ldg(x + j) : __ldg(xg + (j + row0));
-        else
+        if (SHARDED) {
+          if ((uint32_t)j < (uint32_t)n) {
+            xv = __ldg(x + j);
+          } else {
+            xv = __ldcg(xg + (j + row0));  // written by peers: not through the non-coherent path
+            if (rescale) xv = scale_real(xv, inv);
+          }
+        } else {
           xv = __ldg(x + j);
+        }
         acc = add_t(acc, xv);
       }
       pi += 33 + up;
@@ -124,10 +137,16 @@ __global__ void __launch_bounds__(kThreads, 6)
       const int32_t jg = (int32_t)(__ldg(p.rank_lo + (t & lo_mask)) + __ldg(p.rank_hi + (t >> p.half)));
       const int32_t j = jg - row0;
       T xv;
-      if (SHARDED)
-        xv = ((uint32_t)j < (uint32_t)n) ? __ldg(x + j) : __ldg(xg + jg);
-      else
+      if (SHARDED) {
+        if ((uint32_t)j < (uint32_t)n) {
+          xv = __ldg(x + j);
+        } else {
+          xv = __ldcg(xg + jg);
+          if (rescale) xv = scale_real(xv, inv);
+        }
+      } else {
         xv = __ldg(x + j);
+      }
       acc = add_t(acc, xv);
     }
     const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
@@ -146,13 +165,32 @@ struct XxzOpBase : OpBase {
   uint32_t* d_lo = nullptr;
   uint32_t* d_hi = nullptr;
   uint32_t* d_states = nullptr;  // basis states of the local block
-  void* d_xall = nullptr;  // row-sharded runs: gathered input vector (n_global elements)
+  void* d_xall = nullptr;  // row-sharded runs: gathered input vector (n_global elements), NCCL path
   std::vector<size_t> send_off, send_bytes, recv_off, recv_bytes;
+  // fused all-gather: a double-buffered (by message parity) whole-vector buffer on every rank, mapped into every peer
+  ExchangeBuffer* xb = nullptr;
+  PeerMsg cur_gather_msg;  // what the next apply waits for (none: x_all was filled in stream order)
   ~XxzOpBase() override {
     if (d_lo) dev_free(ctx, d_lo);
     if (d_hi) dev_free(ctx, d_hi);
     if (d_xall) dev_free(ctx, d_xall);
     if (d_states) dev_free(ctx, d_states);
+    if (xb) comm_exchange_buffer_release(ctx, xb);
+  }
+  size_t vec_bytes() const { return ((size_t)n_global * dtype_size(dtype) + 255) / 256 * 256; }  // stride between the two copies
+  bool plan_push(GatherPush* push) override {
+    if (!xb) return false;
+    push->msg = comm_next_message(ctx, kChanGather);
+    push->G = ctx->nranks;
+    push->rank = ctx->rank;
+    const size_t off = ((push->msg.seq & 1ull) ? vec_bytes() : 0) + (size_t)row0 * dtype_size(dtype);
+    for (int r = 0; r < ctx->nranks; ++r) push->dst[r] = static_cast<char*>(xb->peer[r]) + off;
+    return true;
+  }
+  void use_pushed(const GatherPush& push, const double* scale) override {
+    prm.x_all = static_cast<char*>(xb->local) + ((push.msg.seq & 1ull) ? vec_bytes() : 0);
+    prm.x_scale = scale;
+    cur_gather_msg = push.msg;
   }
   // every row has at most `nbonds` off-diagonal entries Jxy/2 and a diagonal of magnitude <= nbonds |Jz|/4
   int abs_row_sum_max(double* out) override {
@@ -164,7 +202,15 @@ struct XxzOpBase : OpBase {
   int prepare(const void* x) override {
     if (ctx->nranks == 1) return LLZ_OK;
     ProfScope ps(ctx, "halo", (double)(n_global - n_local) * (double)dtype_size(dtype));
-    return comm_exchange(ctx, (const char*)x, send_off.data(), send_bytes.data(), (char*)d_xall, recv_off.data(), recv_bytes.data());
+    char* dst = (char*)d_xall;
+    if (xb) {  // keep the parity of the exchange buffers alternating with the fused messages
+      const PeerMsg m = comm_next_message(ctx, kChanGather);
+      dst = static_cast<char*>(xb->local) + ((m.seq & 1ull) ? vec_bytes() : 0);
+    }
+    prm.x_all = dst;
+    prm.x_scale = nullptr;
+    cur_gather_msg = PeerMsg();
+    return comm_exchange(ctx, (const char*)x, send_off.data(), send_bytes.data(), dst, recv_off.data(), recv_bytes.data());
   }
 };
 
@@ -175,9 +221,11 @@ template <class T> struct XxzOp : XxzOpBase {
     if (g < 1) g = 1;
     const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
     if (prm.x_all)
-      k_xxz_apply<T, true><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg);
+      k_xxz_apply<T, true><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg,
+                                                              cur_gather_msg);
     else
-      k_xxz_apply<T, false><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg);
+      k_xxz_apply<T, false><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg,
+                                                               PeerMsg());
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_apply: %s", cudaGetErrorString(e));
@@ -267,6 +315,7 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
   op->prm.n = op->n_local;
   op->prm.row0 = op->row0;
   op->prm.x_all = nullptr;
+  op->prm.x_scale = nullptr;
   op->bytes = op->n_local * 4;  // the state table is the only stored part of the operator
   e = dev_malloc(ctx, &op->d_states, sizeof(uint32_t) * (size_t)op->n_local);
   if (e != cudaSuccess) {
@@ -287,12 +336,18 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
   }
   if (ctx->nranks > 1) {
     const size_t es = dtype_size(dtype);
-    e = dev_malloc(ctx, &op->d_xall, (size_t)op->n_global * es);
-    if (e != cudaSuccess) {
-      delete op;
-      return fail(LLZ_ERR_OOM, "op_create_xxz: gathered input vector (%lld elements): %s", (long long)op->n_global, cudaGetErrorString(e));
+    // fused all-gather buffers (two whole vectors, IPC-mapped group-wide) when the group has peer channels; the NCCL
+    // gather then lands in them too.  Otherwise a private gather buffer.
+    const char* env = getenv("LLZ_FUSED_GATHER");
+    if (!(env && env[0] == '0')) op->xb = comm_exchange_buffer_acquire(ctx, 2 * op->vec_bytes());
+    if (!op->xb) {
+      e = dev_malloc(ctx, &op->d_xall, (size_t)op->n_global * es);
+      if (e != cudaSuccess) {
+        delete op;
+        return fail(LLZ_ERR_OOM, "op_create_xxz: gathered input vector (%lld elements): %s", (long long)op->n_global, cudaGetErrorString(e));
+      }
     }
-    op->prm.x_all = op->d_xall;
+    op->prm.x_all = op->xb ? op->xb->local : op->d_xall;
     const int G = ctx->nranks;
     op->send_off.assign(G, 0);
     op->send_bytes.assign(G, (size_t)op->n_local * es);

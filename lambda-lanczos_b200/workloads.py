@@ -65,10 +65,12 @@ def laplacian2d_csr(nx: int, ny: int | None = None, dtype=np.float64):
 
 
 def partition(n: int, rank: int, nranks: int):
-    """Row block of ``rank`` in a group of ``nranks``: (row0, n_local) with row0 = n*rank // nranks — the same
-    arithmetic as ``llz_partition`` (csrc/llz_halo.cpp)."""
-    a = n * rank // nranks
-    b = n * (rank + 1) // nranks
+    """Row block of ``rank`` in a group of ``nranks``: (row0, n_local) with interior boundaries floor(n*r/nranks)
+    rounded down to a multiple of 4 — the same arithmetic as ``llz_partition`` (csrc/llz_halo.cpp)."""
+    def bound(r):
+        return 0 if r <= 0 else n if r >= nranks else (n * r // nranks) & ~3
+
+    a, b = bound(rank), bound(rank + 1)
     return a, b - a
 
 

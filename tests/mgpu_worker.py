@@ -218,6 +218,22 @@ def run_gpu(rank, world):
     g = gather_blocks(dist, torch, np.ascontiguousarray(vec[0]), world, sizes_of(n))
     assert abs(ev[0] - ev_ref[0]) <= 1e-10 * abs(ev_ref[0]) and 1 - abs(np.vdot(vec_ref[0], g)) < 1e-9
 
+    # a sector of odd dimension (L = 13, 6 up spins: 1716 states; L = 7, 3 up: 35 states) — ragged blocks, odd strides
+    for L, n_up in ((13, 6), (7, 3)):
+        opx = pkg.Operator.xxz(ctx, L, n_up=n_up)
+        n = opx.n_global
+        row0, nl = wl.partition(n, rank, world)
+        start = wl.start_vector(n)
+        eng = pkg.LambdaLanczos(opx, n, False, 1)
+        eng.init_vector = start[row0:row0 + nl]
+        ev, vec = eng.run()
+        ref = pkg.LambdaLanczos(pkg.Operator.xxz(solo, L, n_up=n_up), n, False, 1)
+        ref.init_vector = start
+        ev_ref, vec_ref = ref.run()
+        g = gather_blocks(dist, torch, np.ascontiguousarray(vec[0]), world, sizes_of(n))
+        assert abs(ev[0] - ev_ref[0]) <= 1e-10 * abs(ev_ref[0]) and 1 - abs(np.vdot(vec_ref[0], g)) < 1e-9, (L, n_up, ev, ev_ref)
+        assert eng.getIterationCounts() == ref.getIterationCounts(), (eng.getIterationCounts(), ref.getIterationCounts())
+
     L = 14
     opc = pkg.Operator.xxz(ctx, L, dtype=np.complex128)
     n = opc.n_global
@@ -232,6 +248,17 @@ def run_gpu(rank, world):
         assert it == it_ref, (it, it_ref)
     g = gather_blocks(dist, torch, np.ascontiguousarray(cur), world, sizes_of(n))
     assert np.linalg.norm(g - cur_ref) <= 1e-10 * np.linalg.norm(cur_ref)
+    # the same with full reorthogonalisation (the update kernel, not the recurrence kernel, feeds the peers)
+    ex.full_orthogonalize = ex_ref.full_orthogonalize = True
+    it, out = ex.run(-0.25j, psi[row0:row0 + nl].copy())
+    it_ref, out_ref = ex_ref.run(-0.25j, psi.copy())
+    g = gather_blocks(dist, torch, np.ascontiguousarray(out), world, sizes_of(n))
+    assert it == it_ref and np.linalg.norm(g - out_ref) <= 1e-10 * np.linalg.norm(out_ref)
+    # Gerschgorin radius is group-wide
+    full = wl.random_symmetric_csr(3001, 8)
+    r0, nl2 = wl.partition(3001, rank, world)
+    rad = pkg.Operator.csr(ctx, *wl.csr_row_block(*full, r0, nl2), row0=r0, n_cols=3001).gerschgorin_radius()
+    assert abs(rad - pkg.Operator.csr(solo, *full).gerschgorin_radius()) < 1e-12
     ctx.synchronize()
     dist.barrier()
     dist.destroy_process_group()
