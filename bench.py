@@ -166,7 +166,10 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = iters / dt
     sample = (f"same operator and start vector, max_iteration={m} per Lanczos run ({len(r.iter_counts)} runs/step); mv_mul "
-              f"CSR lambda on {threads} thread(s), the reference's vector kernels are single-threaded")
+              f"CSR lambda on {threads} thread(s), the reference's vector kernels are single-threaded.  NOTE: the cost of "
+              f"an iteration grows linearly with its index k (full reorthogonalisation against k vectors), so these first "
+              f"{m} iterations are the CHEAPEST of a run: the GPU arm's workload averages k ~ {args.max_iteration // 2}, where "
+              f"a CPU iteration costs ~{max(1, args.max_iteration // (2 * max(m // 2, 1)))}x more than in this sample")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -192,7 +195,9 @@ def cpu_baseline(args, wl, csr, start):
     dt = time.perf_counter() - t0
     return {"value": sum(r.iter_counts) / dt, "unit": UNIT, "cores": threads, "kind": impl.kind,
             "sample": f"one run() of the same workload with max_iteration={m} ({sum(r.iter_counts)} iterations, {dt:.1f} s); "
-                      f"mv_mul on {threads} thread(s), reference vector kernels single-threaded"}
+                      f"mv_mul on {threads} thread(s), reference vector kernels single-threaded; these are the cheapest "
+                      f"iterations of a run (cost grows linearly with the iteration index k; the GPU workload averages "
+                      f"k ~ {args.max_iteration // 2})"}
 
 
 def run_ours(args, rank, world):
