@@ -272,11 +272,11 @@ __device__ __forceinline__ void finish_scalar(double cta_value, double* partials
 // Store a 128-bit packet of the vector a kernel writes into every peer's exchange buffer as well (fused all-gather).
 template <class T> __device__ __forceinline__ void push_pack(const GatherPush& push, int64_t idx, const Pack<T>& v) {
   for (int p = 0; p < push.G; ++p)
-    if (p != push.rank) st_pack(reinterpret_cast<T*>(push.dst[p]) + idx, v);
+    if (p != push.rank && idx >= push.lo[p] && idx < push.hi[p]) st_pack(reinterpret_cast<T*>(push.dst[p]) + idx, v);
 }
 template <class T> __device__ __forceinline__ void push_guard(const GatherPush& push, int64_t idx, int64_t n, const Pack<T>& v) {
   for (int p = 0; p < push.G; ++p)
-    if (p != push.rank) st_guard(reinterpret_cast<T*>(push.dst[p]), idx, n, v);
+    if (p != push.rank && idx >= push.lo[p] && idx < push.hi[p]) st_guard(reinterpret_cast<T*>(push.dst[p]), idx, n, v);
 }
 
 // Transposed warp reduction: each lane holds M partial sums (M a power of two <= 32); afterwards the total of value

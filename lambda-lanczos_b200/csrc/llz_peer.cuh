@@ -45,6 +45,9 @@ struct GatherPush {
   int G = 0;  // 0 => no push
   int rank = 0;
   void* dst[kMaxRanks] = {};
+  // peer p only needs the local elements [lo[p], hi[p]) (multiples of 4, so whole 128-bit packets); empty: lo >= hi
+  long long lo[kMaxRanks] = {};
+  long long hi[kMaxRanks] = {};
   PeerMsg msg;
 };
 
