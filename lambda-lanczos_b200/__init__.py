@@ -387,7 +387,7 @@ class LambdaLanczos:
         start = None if self.init_vector is None else np.ascontiguousarray(self.init_vector, dtype=op.dtype)
         assert start is None or start.size == n, "init_vector must have the operator's (local) row count"
         evals = np.zeros(self.num_eigs, dtype=np.float64)
-        evecs = np.zeros((self.num_eigs, n), dtype=op.dtype) if self.want_eigenvectors else None
+        evecs = np.empty((self.num_eigs, n), dtype=op.dtype) if self.want_eigenvectors else None
         iters = np.zeros(256, dtype=np.int64)
         n_found, n_runs = i64(0), i64(0)
         stats = RunStats()
@@ -397,7 +397,7 @@ class LambdaLanczos:
         self._iter_counts = [int(x) for x in iters[: n_runs.value]]
         self.stats = stats
         nf = n_found.value
-        return evals[:nf].copy(), (None if evecs is None else evecs[:nf].copy())
+        return evals[:nf].copy(), (None if evecs is None else evecs[:nf])
 
     def getIterationCounts(self):
         return list(self._iter_counts)
