@@ -288,6 +288,138 @@ __global__ void __launch_bounds__(kThreads, 3)
   finish_scalar(t, pa, msg, scratch);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SELL SpMV with the matrix streamed by TMA: the column / value arrays of consecutive slices are contiguous, so a CTA
+// fetches a whole chunk of 16 slices (512 rows) with two `cp.async.bulk` copies into shared memory, completion
+// signalled on an mbarrier, two to three chunks ahead of the warps that consume them.  The matrix stream (94 % of the
+// DRAM bytes of a stencil SpMV) is thereby decoupled from the dependent x gathers: no register staging, no load ->
+// gather round-trip chain per slice, ~100 KB of matrix data in flight per SM.  Same per-row arithmetic as
+// k_sell_spmv_dot (bit-identical y).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTmaChunk = 16;  // slices per chunk: 8 warps x 2 slices
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+template <class T, int STAGES>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_sell_tma_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
+                        const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
+                        T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
+                        PeerMsg halo_msg, int cap /* entries per stage */) {
+  extern __shared__ __align__(128) unsigned char smem_t[];
+  __shared__ double scratch[kWarps];
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ long long sp[STAGES][kTmaChunk + 1];
+  if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t stage_bytes = (size_t)cap * (sizeof(T) + sizeof(int32_t));
+  auto stage_vals = [&](int s) { return reinterpret_cast<T*>(smem_t + (size_t)s * stage_bytes); };
+  auto stage_cols = [&](int s) { return reinterpret_cast<int32_t*>(smem_t + (size_t)s * stage_bytes + (size_t)cap * sizeof(T)); };
+  const int64_t nchunks = (n_slices + kTmaChunk - 1) / kTmaChunk;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // warp 0 fetches chunk number i of this CTA into stage i % STAGES (slice pointers first, then the two bulk copies)
+  auto issue = [&](int64_t i) {
+    const int64_t c = (int64_t)blockIdx.x + i * (int64_t)gridDim.x;
+    if (c >= nchunks) return;
+    const int s = (int)(i % STAGES);
+    const int64_t s0 = c * kTmaChunk;
+    if (lane <= kTmaChunk) {
+      const int64_t at = s0 + lane;
+      sp[s][lane] = __ldg(slice_ptr + (at <= n_slices ? at : n_slices));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const long long p0 = sp[s][0];
+      const uint32_t cnt = (uint32_t)(sp[s][kTmaChunk] - p0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage are done (barrier)
+      mbar_arrive_expect_tx(&full[s], cnt * (uint32_t)(sizeof(T) + sizeof(int32_t)));
+      if (cnt > 0) {
+        bulk_copy_g2s(stage_vals(s), sval + p0, cnt * (uint32_t)sizeof(T), &full[s]);
+        bulk_copy_g2s(stage_cols(s), scol + p0, cnt * (uint32_t)sizeof(int32_t), &full[s]);
+      }
+    }
+  };
+  if (warp == 0)
+    for (int i = 0; i < STAGES - 1; ++i) issue(i);
+  double dot = 0.0;
+  for (int64_t i = 0;; ++i) {
+    const int64_t c = (int64_t)blockIdx.x + i * (int64_t)gridDim.x;
+    if (c >= nchunks) break;
+    const int s = (int)(i % STAGES);
+    const uint32_t parity = (uint32_t)((i / STAGES) & 1);
+    if (warp == 0) issue(i + STAGES - 1);  // refills the stage every warp finished with at the end of the last turn
+    while (!mbar_try_wait(&full[s], parity)) {
+    }
+    const T* __restrict__ vs = stage_vals(s);
+    const int32_t* __restrict__ cs = stage_cols(s);
+    const long long base = sp[s][0];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int q = warp * 2 + u;
+      const int64_t slice = c * kTmaChunk + q;
+      if (slice >= n_slices) continue;
+      const int off = (int)(sp[s][q] - base) + lane;
+      const int w = (int)((sp[s][q + 1] - sp[s][q]) / kSellC);
+      T sum = zero_of(T());
+      int j = 0;
+      for (; j + 4 <= w; j += 4) {
+        int32_t cc[4];
+        T vv[4], xv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          cc[t] = cs[off + (j + t) * kSellC];
+          vv[t] = vs[off + (j + t) * kSellC];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) xv[t] = cc[t] >= 0 ? gather_x(x, halo, cc[t], nloc) : zero_of(T());
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (cc[t] >= 0) sum = add_rn(sum, mul_rn(vv[t], xv[t]));
+      }
+      for (; j < w; ++j) {
+        const int32_t cc = cs[off + j * kSellC];
+        const T vv = vs[off + j * kSellC];
+        if (cc >= 0) sum = add_rn(sum, mul_rn(vv, gather_x(x, halo, cc, nloc)));
+      }
+      const int64_t r = slice * kSellC + lane;
+      if (r < n) {
+        const int64_t out = perm ? perm[r] : r;
+        const T xi = x[out];
+        const T yi = add_t(sum, scale_real(xi, sigma));
+        y[out] = yi;
+        dot += re_conj_mul(xi, yi);
+      }
+    }
+    __syncthreads();  // every warp is done with stage s (and its slice pointers) before warp 0 refills it
+  }
+  const double t = block_sum(dot, scratch);
+  finish_scalar(t, pa, msg, scratch);
+}
+
 // Gerschgorin radius: per-CTA maximum of the absolute row sums (CSR: one thread per row; SELL: one lane per row).
 template <class T, class IDX>
 __global__ void __launch_bounds__(kThreads) k_csr_rowsum_max(const IDX* __restrict__ rowptr, const T* __restrict__ vals, int64_t n, double* out) {
@@ -357,6 +489,8 @@ template <class T> struct CsrOp : OpBase {
   int32_t* d_scol = nullptr;
   T* d_sval = nullptr;
   int32_t* d_perm = nullptr;  // null when rows are not sorted (sigma = 1)
+  int tma_cap = 0;            // > 0: entries per shared-memory stage of the TMA-streamed kernel; 0: register-staged kernel
+  int tma_stages = 0;
 
   ~CsrOp() override {
     if (d_slice_ptr) dev_free(ctx, d_slice_ptr);
@@ -452,7 +586,25 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
 
+  template <int STAGES> int launch_sell_tma(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
+    const size_t smem = (size_t)STAGES * tma_cap * (sizeof(T) + sizeof(int32_t));
+    cudaError_t e = cudaFuncSetAttribute(k_sell_tma_spmv_dot<T, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "cudaFuncSetAttribute(k_sell_tma_spmv_dot, %zu): %s", smem, cudaGetErrorString(e));
+    const int64_t nchunks = (n_slices + kTmaChunk - 1) / kTmaChunk;
+    const int per_sm = smem * 2 <= 200 * 1024 ? 2 : 1;
+    int64_t g = std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)ctx->num_sms * per_sm));
+    k_sell_tma_spmv_dot<T, STAGES><<<(int)g, kThreads, smem, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo,
+                                                                          nloc32(), (T*)y, n_local, n_slices, (typename Num<T>::R)sigma,
+                                                                          pa, msg, cur_halo_msg, tma_cap);
+    *npa = (int)g;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_sell_tma_spmv_dot: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return LLZ_OK;
+  }
+
   int launch_sell(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
+    if (tma_cap > 0) return tma_stages >= 3 ? launch_sell_tma<3>(x, y, sigma, pa, npa, msg) : launch_sell_tma<2>(x, y, sigma, pa, npa, msg);
     const int64_t per_cta = kWarps * 2;  // slices one CTA covers per step
     int64_t g = std::min<int64_t>((n_slices + per_cta - 1) / per_cta, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
@@ -529,6 +681,18 @@ template <class T> struct CsrOp : OpBase {
     padded_nnz = total;
     std::vector<int64_t> sp((size_t)n_slices + 1, 0);
     for (int64_t i = 0; i < n_slices; ++i) sp[(size_t)i + 1] = sp[(size_t)i] + (int64_t)width[(size_t)i] * kSellC;
+    {  // TMA-streamed kernel: the largest chunk of 16 slices must fit a shared-memory stage, >= 2 stages in <= 200 KB
+      int64_t worst = 0;
+      for (int64_t c0 = 0; c0 < n_slices; c0 += kTmaChunk)
+        worst = std::max(worst, sp[(size_t)std::min<int64_t>(n_slices, c0 + kTmaChunk)] - sp[(size_t)c0]);
+      const size_t stage = (size_t)worst * (sizeof(T) + sizeof(int32_t));
+      const char* env = getenv("LLZ_SELL_TMA");
+      tma_cap = 0;
+      if ((env && env[0] == '1') && worst > 0 && stage * 2 <= 200 * 1024) {  // opt-in until validated on hardware
+        tma_cap = (int)worst;
+        tma_stages = stage * 3 <= 100 * 1024 ? 3 : (stage * 3 <= 200 * 1024 && stage * 2 > 100 * 1024 ? 3 : 2);
+      }
+    }
     cudaError_t e = dev_malloc(ctx, &d_slice_ptr, sizeof(int64_t) * sp.size());
     if (e == cudaSuccess) e = dev_malloc(ctx, &d_scol, std::max<size_t>(16, sizeof(int32_t) * (size_t)total));
     if (e == cudaSuccess) e = dev_malloc(ctx, &d_sval, std::max<size_t>(16, sizeof(T) * (size_t)total));
