@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(kThreads) k_sell_fill(const IDX* __restrict__ 
 // Each warp walks TWO adjacent slices per step (64 rows: 2 x 5 x 384 B of matrix data in flight per warp on a 5-point
 // stencil) and fetches the slice pointers of its next step before it starts on the current one, so the three dependent
 // round trips (slice pointer -> column/value -> x gather) of consecutive steps overlap.
-template <class T>
-__global__ void __launch_bounds__(kThreads, 3)
+template <class T, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
                     const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
                     T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
@@ -608,8 +608,15 @@ template <class T> struct CsrOp : OpBase {
     const int64_t per_cta = kWarps * 2;  // slices one CTA covers per step
     int64_t g = std::min<int64_t>((n_slices + per_cta - 1) / per_cta, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_sell_spmv_dot<T><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(), (T*)y,
-                                                            n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
+    // real element types fit 64 registers (4 resident CTAs, more loads in flight); complex ones need 80 (3 CTAs)
+    static const int env_blocks = getenv("LLZ_SELL_BLOCKS") ? atoi(getenv("LLZ_SELL_BLOCKS")) : 0;
+    const int blocks = env_blocks ? env_blocks : (Num<T>::NC == 1 ? 4 : 3);
+    if (blocks >= 4)
+      k_sell_spmv_dot<T, 4><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(), (T*)y,
+                                                                 n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
+    else
+      k_sell_spmv_dot<T, 3><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(), (T*)y,
+                                                                 n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     *npa = (int)g;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_sell_spmv_dot: %s", cudaGetErrorString(e));
