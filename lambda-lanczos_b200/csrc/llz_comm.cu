@@ -232,7 +232,6 @@ static int p2p_setup(llz_ctx_t ctx) {
 
 bool comm_p2p(llz_ctx_t ctx) { return ctx->nranks > 1 && ctx->comm && ctx->comm->ch[0].G > 0; }
 int comm_coef_capacity(llz_ctx_t ctx) { return comm_p2p(ctx) ? kCoefPayload : 0; }
-unsigned int* comm_ticket(llz_ctx_t ctx) { return comm_p2p(ctx) ? ctx->comm->ticket : nullptr; }
 
 // Halo window of this rank: first-fit sub-allocation (256-byte granularity); returns the offset inside the window or
 // -1 when there is no peer window or no room (the operator then uses the NCCL exchange).

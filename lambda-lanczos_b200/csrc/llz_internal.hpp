@@ -154,7 +154,6 @@ void comm_destroy(llz_ctx_t ctx);
 // Peer-memory channels (llz_peer.cuh) set up by llz_ctx_join: 0 = alpha, 1 = beta^2, 2 = projection coefficients
 bool comm_p2p(llz_ctx_t ctx);
 int comm_coef_capacity(llz_ctx_t ctx);
-unsigned int* comm_ticket(llz_ctx_t ctx);
 int comm_check_peers(llz_ctx_t ctx);
 // Whole-vector exchange buffers for the fused all-gather (llz_comm.cu)
 struct ExchangeBuffer {

@@ -240,19 +240,6 @@ __global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
   }
 }
 
-// One CTA: group-wide delivery of a scalar that exists as per-CTA partials (alpha after the operator, ||u||^2 after the
-// update).  Thread p stores to rank p, fences and announces.
-__global__ void __launch_bounds__(kThreads) k_push_scalar(const double* __restrict__ partials, int count, PeerMsg msg) {
-  __shared__ double scratch[kWarps];
-  const double v = block_sum_partials(partials, count, scratch);
-  const int p = threadIdx.x;
-  if (p < msg.ch.G) {
-    peer_slot(msg.ch, p, msg.seq, msg.ch.rank)[0] = v;
-    __threadfence_system();
-    peer_announce(msg.ch, p, msg.seq);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 struct UpdateArgs {
   const void* V;
@@ -846,11 +833,6 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
   a.ticket = msg.ticket;
   k_reduce<<<(a.width + 1 + 31) / 32, kThreads, 0, ctx->stream>>>(a);
   return check_launch(ctx, "k_reduce");
-}
-
-int launch_push_scalar(llz_ctx_t ctx, const double* partials, int count, const PeerMsg& msg) {
-  k_push_scalar<<<1, kThreads, 0, ctx->stream>>>(partials, count, msg);
-  return check_launch(ctx, "k_push_scalar");
 }
 
 template <class T, int VPT>

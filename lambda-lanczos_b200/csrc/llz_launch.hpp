@@ -66,8 +66,6 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
 // message is announced when `publish` is set (last chunk of a pass).
 int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2,
                   const PeerMsg& msg = PeerMsg(), int wnorm_index = -1, int publish = 0);
-// One CTA: sums `count` per-CTA partials and delivers the result as element 0 of message `msg` to every rank.
-int launch_push_scalar(llz_ctx_t ctx, const double* partials, int count, const PeerMsg& msg);
 // out = w' - sum_j coef_j col_j over the chunk [col0, col0+ncols), where w' = w - alpha u_{k-1} - beta u_{k-2} per `fold`
 // (then the chunk must EXCLUDE those fold.mode trailing basis columns: the kernel applies their coefficients itself).
 // If norm_partials != null, per-CTA partials of ||out||^2.
