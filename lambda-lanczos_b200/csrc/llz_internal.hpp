@@ -155,6 +155,10 @@ void comm_destroy(llz_ctx_t ctx);
 bool comm_p2p(llz_ctx_t ctx);
 int comm_coef_capacity(llz_ctx_t ctx);
 int comm_check_peers(llz_ctx_t ctx);
+// Halo planning (llz_halo.cpp): one pass producing the sorted unique remote columns, their count per owner and the
+// column indices in the local extended numbering.
+int halo_plan_vectors(int64_t n_rows, int64_t row0, const int64_t* rowptr, const int32_t* colidx, int nranks,
+                      const int64_t* boundaries, int32_t* colidx_local, std::vector<int32_t>& remote, int64_t* per_owner);
 // Whole-vector exchange buffers for the fused all-gather (llz_comm.cu)
 struct ExchangeBuffer {
   size_t bytes = 0;

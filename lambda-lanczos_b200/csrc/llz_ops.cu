@@ -770,11 +770,10 @@ static int plan_sharded_csr(CsrOp<T>* op, int64_t row0, const int64_t* rowptr, c
   if (bounds[G] != op->n_cols) return fail(LLZ_ERR_INVALID, "csr: the row blocks cover %lld rows, the operator has %lld columns", (long long)bounds[G], (long long)op->n_cols);
   const int64_t nnz = rowptr[n_rows];
   col_local.resize((size_t)std::max<int64_t>(nnz, 1));
-  int64_t n_halo = 0;
   std::vector<int64_t> need((size_t)G, 0);
-  LLZ_TRY(llz_halo_plan(n_rows, row0, rowptr, colidx, G, bounds.data(), nullptr, nullptr, 0, &n_halo, nullptr));
-  std::vector<int64_t> halo_cols((size_t)std::max<int64_t>(n_halo, 1));
-  LLZ_TRY(llz_halo_plan(n_rows, row0, rowptr, colidx, G, bounds.data(), col_local.data(), halo_cols.data(), n_halo, &n_halo, need.data()));
+  std::vector<int32_t> halo_cols;
+  LLZ_TRY(halo_plan_vectors(n_rows, row0, rowptr, colidx, G, bounds.data(), col_local.data(), halo_cols, need.data()));
+  const int64_t n_halo = (int64_t)halo_cols.size();
   // need_all[q*G + p] = number of entries rank q needs from rank p
   std::vector<int64_t> need_all((size_t)G * G);
   LLZ_TRY(comm_allgather_host(ctx, need.data(), need_all.data(), sizeof(int64_t) * G));

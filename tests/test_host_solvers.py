@@ -65,6 +65,58 @@ def test_extreme_sequence_warm_start_equals_cold(host, find_max):
         assert np.allclose(seq[m - 1, :k], want, rtol=0, atol=4e-15 * np.abs(exact).max()), m
 
 
+def real_lanczos_recurrence(kind, m, seed):
+    """alpha/beta of an actual (fully reorthogonalised) Lanczos run: converging extreme Ritz values, the regime the
+    predicted brackets are built for — including a deflated operator with (near-)degenerate values and a breakdown."""
+    rs = np.random.RandomState(seed)
+    if kind == "clustered":  # spectrum with tight clusters at both ends
+        n = 400
+        lam = np.concatenate([[-3.0, -3.0 + 1e-9, -3.0 + 2e-9, -2.5], rs.uniform(-1, 1, n - 8), [2.5, 3.0 - 2e-10, 3.0 - 1e-10, 3.0]])
+    elif kind == "lowrank":  # Krylov space exhausts after 12 steps: beta collapses to rounding level
+        n = 300
+        lam = np.repeat(np.linspace(-1, 2, 12), n // 12)
+    else:  # 1-D Laplacian-like: many slowly converging values
+        n = 600
+        lam = 2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    n = lam.size
+    v = rs.uniform(-1, 1, n)
+    v /= np.linalg.norm(v)
+    V = [v]
+    alpha, beta = [], []
+    for k in range(m):
+        w = lam * V[-1]
+        alpha.append(float(w @ V[-1]))
+        B = np.array(V)
+        w = w - B.T @ (B @ w)
+        w = w - B.T @ (B @ w)
+        b = float(np.linalg.norm(w))
+        beta.append(b)
+        if b < 1e-13:
+            break
+        V.append(w / b)
+    return np.array(alpha), np.array(beta)
+
+
+@pytest.mark.parametrize("kind,m", [("clustered", 160), ("lowrank", 40), ("laplacian", 250)])
+@pytest.mark.parametrize("find_max", [False, True])
+@pytest.mark.parametrize("nroot", [1, 5, 8])
+def test_predicted_brackets_never_lose_a_root(host, kind, m, find_max, nroot):
+    """The warm-started solver (brackets predicted from the previous iteration, checked by Sturm counts) must return
+    what a cold bisection of every prefix T_1..T_m returns, on recurrences of real Lanczos runs."""
+    alpha, beta = real_lanczos_recurrence(kind, m, 3)
+    mm = alpha.size
+    seq = np.zeros((mm, nroot))
+    host.ht_extreme_sequence(p(alpha), p(beta), C.c_int64(mm), C.c_int64(nroot), C.c_int(int(find_max)), p(seq))
+    for k in range(1, mm + 1):
+        cold = np.zeros(min(nroot, k))
+        host.ht_extreme(p(alpha), p(beta), C.c_int64(k), C.c_int64(min(nroot, k)), C.c_int(int(find_max)), p(cold))
+        scale = max(1.0, np.abs(alpha[:k]).max() + 2 * np.abs(beta[:k]).max())
+        assert np.allclose(seq[k - 1, : cold.size], cold, rtol=0, atol=8e-16 * scale), (kind, k)
+    exact = np.linalg.eigvalsh(dense(alpha, beta))
+    want = exact[::-1][:nroot] if find_max else exact[:nroot]
+    assert np.allclose(seq[mm - 1, : want.size], want[: min(nroot, mm)], rtol=0, atol=1e-13 * np.abs(exact).max())
+
+
 def test_extreme_eigenvalues_clustered_and_tiny_couplings(host):
     # nearly decoupled blocks => nearly degenerate extreme values; Sturm counts must still separate them
     alpha = np.array([1.0, 1.0, 1.0 + 1e-13, 3.0, 3.0, -2.0])
