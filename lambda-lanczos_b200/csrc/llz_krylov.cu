@@ -420,6 +420,14 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   llz_ctx_t ctx = kry->ctx;
   LLZ_CUDA(cudaSetDevice(ctx->device));
   LLZ_CUDA(cudaStreamSynchronize(ctx->stream));  // nothing of a previous run may still publish scalars
+  if (ctx->nranks > 1) {
+    // Row-sharded: line the ranks up on the host before the first kernel that waits for a peer's message, so that a
+    // rank that arrives late (still building its operator, reading input ...) makes the others wait here, in a
+    // collective, and not inside a spinning kernel with a time-out.
+    LLZ_CUDA(cudaMemsetAsync(kry->d_misc + 2, 0, sizeof(double), ctx->stream));
+    LLZ_TRY(comm_allreduce_sum(ctx, kry->d_misc + 2, 1));
+    LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   kry->k = 0;
   kry->pushed_valid = false;
   kry->h_flag[0] = 0;

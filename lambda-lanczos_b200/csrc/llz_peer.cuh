@@ -79,8 +79,8 @@ __device__ __forceinline__ void peer_announce(const PeerChannel& ch, int p, unsi
 }
 
 // Called by ALL threads of a CTA (blockDim >= G): returns once message `seq` of every rank has landed in the local
-// inbox.  Gives up after ~20 s (a peer process died) and raises the status word so the host reports it instead of
-// hanging the GPU.
+// inbox.  Gives up after ~2 minutes (a peer process died) and raises the status word so the host reports it instead
+// of hanging the GPU for ever.
 __device__ __forceinline__ void peer_wait(const PeerChannel& ch, unsigned long long seq) {
   if ((int)threadIdx.x < ch.G) {
     const unsigned long long* f = peer_flag(ch, ch.rank, seq, threadIdx.x);
@@ -90,7 +90,7 @@ __device__ __forceinline__ void peer_wait(const PeerChannel& ch, unsigned long l
       while (ld_acquire_sys(f) < seq) {
         if ((++spins & 0xfff) == 0) {
           if (ch.status && *reinterpret_cast<volatile unsigned long long*>(ch.status) != 0) break;  // already failed
-          if (global_timer_ns() - t0 > 20000000000ull) {
+          if (global_timer_ns() - t0 > 120000000000ull) {
             if (ch.status) atomicExch(ch.status, seq | (1ull << 63));
             break;
           }
