@@ -1,10 +1,13 @@
-// llz_comm.cu — inter-GPU plumbing for row-sharded runs: one process per GPU, one NCCL communicator per context,
-// all collectives enqueued on the context's stream (NVLink 5 / NVSwitch underneath).  Single-rank contexts never
-// reach NCCL.
+// llz_comm.cu — inter-GPU plumbing for row-sharded runs: one process per GPU of one box.
 //
-// Per Lanczos iteration a joined context issues: one halo exchange before the SpMV (only the remote entries the local
-// rows reference, ncclSend/ncclRecv grouped), one all-reduce of the packed projection coefficients, and all-reduces of
-// the alpha / beta^2 scalars.
+//   * an NCCL communicator per joined context (bound at run time, see NcclApi) for set-up traffic, stand-alone vector
+//     reductions and as the fall-back transport;
+//   * CUDA-IPC mapped peer memory for everything inside the Lanczos iteration (llz_peer.cuh): the scalar channels
+//     (alpha, beta^2, projection coefficients, halo / gather announcements), a halo window that row-sharded CSR / SELL
+//     operators sub-allocate, and whole-vector exchange buffers for operators that read the entire input vector.
+//     Producing kernels store into the peers' memory over NVLink and consuming kernels wait in their prologue, so a
+//     sharded iteration issues no collective call at all.
+// Single-rank contexts never reach any of this.
 #include <dlfcn.h>
 #include <nccl.h>  // types and enums only: the library itself is bound at run time (see NcclApi)
 

@@ -1,6 +1,8 @@
 // llz_ops.cu — device operators: the replacement of the reference's `mv_mul` std::function
-// (lambda_lanczos.hpp:120-126, exponentiator.hpp:35-41).  Built-in CSR SpMV with the alpha = Re<x, A x> dot fused
-// into its epilogue, and the user callback adapter.  (The matrix-free XXZ operator lives in llz_xxz.cu.)
+// (lambda_lanczos.hpp:120-126, exponentiator.hpp:35-41).  Built-in CSR (lanes-per-row and stream kernels) and
+// SELL-32-sigma (register-staged and TMA-streamed kernels) SpMV with the alpha = Re<x, A x> dot fused into the
+// epilogue, the halo exchange of their row-sharded form, the Gerschgorin row-sum kernels and the user callback
+// adapter.  (The matrix-free XXZ operator lives in llz_xxz.cu.)
 #include <algorithm>
 #include <cstdlib>
 #include <vector>

@@ -2,9 +2,11 @@
 //     H = sum_<i,i+1> [ Jxy/2 (S+_i S-_{i+1} + h.c.) + Jz Sz_i Sz_{i+1} ]
 // on L sites, basis = all L-bit integers with n_up set bits in increasing order.  Nothing of the matrix is stored:
 // y_r = diag(s_r) x_r + Jxy/2 * sum_{anti-parallel bonds b of s_r} x[rank(s_r ^ flip_b)]   (H is symmetric, so the
-// gather form needs no atomics).  rank() is the combinatorial number system evaluated with two Lin tables (low / high
-// half of the bit string, 2^(L/2) entries each — they live in L1/L2); each thread unranks the first of ITEMS
-// consecutive states once and steps to the next ones with Gosper's bit trick.
+// gather form needs no atomics).  The basis states come from a 4-byte-per-row table built on the device (one
+// unranking per 32 states, Gosper steps between); the rank of a flipped state is the row index plus or minus a
+// binomial coefficient (k_xxz_apply), the two Lin tables (low / high half of the bit string, 2^(L/2) entries each)
+// only serve the periodic wrap bond.  Row-sharded, the block reads index ranges of x owned by other ranks: they arrive
+// either pushed by the kernel that produced x (fused all-gather, llz_peer.cuh) or by grouped send/recv.
 // The alpha = Re<x, Hx> dot is fused into the epilogue like the CSR kernel's.
 #include <algorithm>
 #include <cmath>
