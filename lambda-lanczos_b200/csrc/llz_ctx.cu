@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "llz_launch.hpp"
@@ -147,6 +148,10 @@ int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
   ctx->vec_pool_limit = (size_t)prop.totalGlobalMem / 4;
+  {
+    const char* env = getenv("LLZ_PDL");
+    ctx->pdl = env && env[0] == '1';  // opt-in: measured 6 % SLOWER on config 1 (9.9k vs 10.6k it/s), neutral elsewhere
+  }
   if (cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;

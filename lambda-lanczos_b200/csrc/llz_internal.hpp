@@ -81,6 +81,7 @@ struct llz_ctx_s {
   size_t vec_pool_bytes = 0;
   size_t vec_pool_limit = 0;              // set at creation (a quarter of the device memory)
   llz_krylov_t cached_krylov = nullptr;   // last destroyed Krylov workspace, revived by a matching llz_krylov_create
+  bool pdl = false;  // programmatic dependent launch between the kernels of an iteration (LLZ_PDL=1 switches it on)
   // profiling
   bool profile = false;
   std::map<std::string, llz::ProfEntry> prof;

@@ -133,6 +133,7 @@ __device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base,
 
 template <class T, int VPT>
 __global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
+  pdl_prologue();
   using R = typename Num<T>::R;
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
   extern __shared__ __align__(16) double smem_d[];
@@ -198,6 +199,7 @@ struct ReduceArgs {
 // are added in a fixed order.  Row-sharded: the result goes straight into every peer's inbox over NVLink and the last
 // CTA to finish announces the message — no collective call between the projection and the update.
 __global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
+  pdl_prologue();
   __shared__ double part[kWarps][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
@@ -361,6 +363,7 @@ __device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base,
 
 template <class T, int VPT>
 __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
+  pdl_prologue();
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
   extern __shared__ __align__(16) unsigned char smem_u[];
   T* cs = reinterpret_cast<T*>(smem_u);
@@ -414,6 +417,7 @@ struct ScaleNormArgs {
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(ScaleNormArgs a) {
+  pdl_prologue();
   using R = typename Num<T>::R;
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
@@ -476,6 +480,7 @@ struct RecurrenceArgs {
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
+  pdl_prologue();
   using R = typename Num<T>::R;
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
@@ -669,6 +674,7 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_dot(const T*
 }
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const T* __restrict__ x, const T* __restrict__ y, int64_t n, double* partials, PeerMsg msg) {
+  pdl_prologue();
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
   double re = 0.0;
@@ -781,8 +787,9 @@ static int project_impl(llz_ctx_t ctx, const ProjectArgs& a, int* grid_out) {
   LLZ_TRY(set_smem(k_project<T, VPT>, smem));
   const int64_t nslabs = (a.n + slab_rows<T>(VPT) - 1) / slab_rows<T>(VPT);
   const int grid = persistent_grid(ctx, nslabs, 2);
-  k_project<T, VPT><<<grid, kThreads, smem, ctx->stream>>>(a);
+  cudaError_t le = launch_chain(ctx, k_project<T, VPT>, grid, kThreads, smem, a);
   *grid_out = grid;
+  if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_project: %s", cudaGetErrorString(le));
   return check_launch(ctx, "k_project");
 }
 
@@ -831,7 +838,8 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
   a.wnorm_index = wnorm_index;
   a.publish = publish;
   a.ticket = msg.ticket;
-  k_reduce<<<(a.width + 1 + 31) / 32, kThreads, 0, ctx->stream>>>(a);
+  cudaError_t le = launch_chain(ctx, k_reduce, (a.width + 1 + 31) / 32, kThreads, 0, a);
+  if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_reduce: %s", cudaGetErrorString(le));
   return check_launch(ctx, "k_reduce");
 }
 
@@ -841,8 +849,9 @@ static int update_impl(llz_ctx_t ctx, const UpdateArgs& a, int* grid_out) {
   LLZ_TRY(set_smem(k_update<T, VPT>, smem));
   const int64_t nslabs = (a.n + slab_rows<T>(VPT) - 1) / slab_rows<T>(VPT);
   const int grid = persistent_grid(ctx, nslabs, 2);
-  k_update<T, VPT><<<grid, kThreads, smem, ctx->stream>>>(a);
+  cudaError_t le = launch_chain(ctx, k_update<T, VPT>, grid, kThreads, smem, a);
   *grid_out = grid;
+  if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_update: %s", cudaGetErrorString(le));
   return check_launch(ctx, "k_update");
 }
 
@@ -893,7 +902,8 @@ int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const dou
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
     const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
-    k_scale_norm<T><<<grid, kThreads, 0, ctx->stream>>>(a);
+    cudaError_t le = launch_chain(ctx, k_scale_norm<T>, grid, kThreads, 0, a);
+    if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_scale_norm: %s", cudaGetErrorString(le));
   });
   return check_launch(ctx, "k_scale_norm");
 }
@@ -918,7 +928,8 @@ int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, c
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
     const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
-    k_recurrence<T><<<grid, kThreads, 0, ctx->stream>>>(a);
+    cudaError_t le = launch_chain(ctx, k_recurrence<T>, grid, kThreads, 0, a);
+    if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_recurrence: %s", cudaGetErrorString(le));
     *grid_out = grid;
   });
   return check_launch(ctx, "k_recurrence");
@@ -973,7 +984,8 @@ int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t
   LLZ_DISPATCH(dtype, {
     const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
     const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
-    k_redot<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)a, (const T*)b, n, partials, msg);
+    cudaError_t le = launch_chain(ctx, k_redot<T>, grid, kThreads, 0, (const T*)a, (const T*)b, n, partials, msg);
+    if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_redot: %s", cudaGetErrorString(le));
     *grid_out = grid;
   });
   return check_launch(ctx, "k_redot");

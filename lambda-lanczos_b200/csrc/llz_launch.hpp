@@ -1,9 +1,34 @@
 // llz_launch.hpp — typed-erased launchers of the streaming kernels (llz_kernels.cu).  All launch on ctx->stream.
 #pragma once
+#include <cstring>
+
 #include "llz_internal.hpp"
 #include "llz_peer.cuh"
 
 namespace llz {
+
+#ifdef __CUDACC__
+// Launch a kernel of the per-iteration chain: a plain launch, or with programmatic stream serialisation (see
+// pdl_prologue in llz_device.cuh) when the context has it switched on (LLZ_PDL=1).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(llz_ctx_t ctx, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
+  if (!ctx->pdl) {
+    kernel<<<grid, block, smem, ctx->stream>>>(KArgs(args)...);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // The NEXT message of a peer channel (llz_comm.cu; every rank calls this in the same order); unused (ch.G == 0) when
 // the context has no peer channels.

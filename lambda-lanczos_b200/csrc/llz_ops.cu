@@ -50,6 +50,7 @@ struct HaloPush {
 template <class T>
 __global__ void __launch_bounds__(kThreads) k_halo_push(const T* __restrict__ x, const int32_t* __restrict__ idx, long long n_send, HaloPush hp, PeerMsg msg) {
   __shared__ int last_cta;
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_send; i += (long long)gridDim.x * kThreads) {
     int q = 0;
     while (i >= hp.start[q + 1]) ++q;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 4)
                    const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
                    typename Num<T>::R sigma, double* pa, PeerMsg msg, PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
+  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);  // the peers' entries of x have landed in `halo`
   constexpr int ROWS = kThreads / LPR;
   const int tid = threadIdx.x;
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 4)
                      const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
                      typename Num<T>::R sigma, double* pa, int R, int cap, PeerMsg msg, PeerMsg halo_msg) {
   extern __shared__ __align__(16) unsigned char smem_s[];
+  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   T* prod = reinterpret_cast<T*>(smem_s);
   IDX* rp = reinterpret_cast<IDX*>(prod + cap);
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
                     T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
                     PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
+  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   constexpr int U = 2;  // slices per warp step
   const int lane = threadIdx.x & 31;
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   __shared__ double scratch[kWarps];
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ long long sp[STAGES][kTmaChunk + 1];
+  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t stage_bytes = (size_t)cap * (sizeof(T) + sizeof(int32_t));
@@ -521,8 +526,7 @@ template <class T> struct CsrOp : OpBase {
       if (m.seq & 1ull)
         for (int q = 0; q < hp.G; ++q) hp.dst[q] = static_cast<char*>(hp.dst[q]) + push_stride[q];
       const int64_t g = std::max<int64_t>(1, std::min<int64_t>((n_send + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 2));
-      k_halo_push<T><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, d_send_idx, (long long)n_send, hp, m);
-      cudaError_t e = cudaGetLastError();
+      cudaError_t e = launch_chain(ctx, k_halo_push<T>, (int)g, kThreads, 0, (const T*)x, d_send_idx, (long long)n_send, hp, m);
       if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_halo_push: %s", cudaGetErrorString(e));
       ctx->launches++;
       cur_halo = reinterpret_cast<const T*>(static_cast<char*>(comm_window_ptr(ctx, ctx->rank, win_off)) +
@@ -548,11 +552,9 @@ template <class T> struct CsrOp : OpBase {
     int64_t blocks = (n_local + ROWS - 1) / ROWS;
     int64_t g = std::min<int64_t>(blocks, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_csr_spmv_dot<T, IDX, LPR><<<(int)g, kThreads, 0, ctx->stream>>>(
-        (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, cur_halo, nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa, msg,
-        cur_halo_msg);
+    cudaError_t e = launch_chain(ctx, k_csr_spmv_dot<T, IDX, LPR>, (int)g, kThreads, 0, (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x,
+                                 cur_halo, nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     *npa = (int)g;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_csr_spmv_dot: %s", cudaGetErrorString(e));
     ctx->launches++;
     return LLZ_OK;
@@ -578,11 +580,10 @@ template <class T> struct CsrOp : OpBase {
     const int64_t blocks = (n_local + stream_rows - 1) / stream_rows;
     int64_t g = std::min<int64_t>(blocks, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
     if (g < 1) g = 1;
-    k_csr_stream_dot<T, IDX><<<(int)g, kThreads, smem, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x, cur_halo,
-                                                                     nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa,
-                                                                     stream_rows, stream_cap, msg, cur_halo_msg);
+    cudaError_t e = launch_chain(ctx, k_csr_stream_dot<T, IDX>, (int)g, kThreads, smem, (const IDX*)d_rowptr, d_colidx, d_vals, (const T*)x,
+                                 cur_halo, nloc32(), (T*)y, n_local, (typename Num<T>::R)sigma, pa, stream_rows, stream_cap, msg,
+                                 cur_halo_msg);
     *npa = (int)g;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_csr_stream_dot: %s", cudaGetErrorString(e));
     ctx->launches++;
     return LLZ_OK;
@@ -595,11 +596,9 @@ template <class T> struct CsrOp : OpBase {
     const int64_t nchunks = (n_slices + kTmaChunk - 1) / kTmaChunk;
     const int per_sm = smem * 2 <= 200 * 1024 ? 2 : 1;
     int64_t g = std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)ctx->num_sms * per_sm));
-    k_sell_tma_spmv_dot<T, STAGES><<<(int)g, kThreads, smem, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo,
-                                                                          nloc32(), (T*)y, n_local, n_slices, (typename Num<T>::R)sigma,
-                                                                          pa, msg, cur_halo_msg, tma_cap);
+    e = launch_chain(ctx, k_sell_tma_spmv_dot<T, STAGES>, (int)g, kThreads, smem, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo,
+                     nloc32(), (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg, tma_cap);
     *npa = (int)g;
-    e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_sell_tma_spmv_dot: %s", cudaGetErrorString(e));
     ctx->launches++;
     return LLZ_OK;
@@ -613,14 +612,14 @@ template <class T> struct CsrOp : OpBase {
     // real element types fit 64 registers (4 resident CTAs, more loads in flight); complex ones need 80 (3 CTAs)
     static const int env_blocks = getenv("LLZ_SELL_BLOCKS") ? atoi(getenv("LLZ_SELL_BLOCKS")) : 0;
     const int blocks = env_blocks ? env_blocks : (Num<T>::NC == 1 ? 4 : 3);
+    cudaError_t e;
     if (blocks >= 4)
-      k_sell_spmv_dot<T, 4><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(), (T*)y,
-                                                                 n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
+      e = launch_chain(ctx, k_sell_spmv_dot<T, 4>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
+                       (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     else
-      k_sell_spmv_dot<T, 3><<<(int)g, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(), (T*)y,
-                                                                 n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
+      e = launch_chain(ctx, k_sell_spmv_dot<T, 3>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
+                       (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     *npa = (int)g;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_sell_spmv_dot: %s", cudaGetErrorString(e));
     ctx->launches++;
     return LLZ_OK;

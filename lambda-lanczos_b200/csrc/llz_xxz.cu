@@ -83,12 +83,13 @@ __global__ void __launch_bounds__(kThreads, 6)
                 typename Num<T>::R sigma, double* pa, PeerMsg msg, PeerMsg gather_msg) {
   using R = typename Num<T>::R;
   __shared__ double scratch[kWarps];
-  __shared__ uint32_t pascal[32 * 33];
+  __shared__ uint32_t pascal[32 * 33];  // pascal[b*33 + c] = C(b, c); the odd stride spreads rows over the banks
+  for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
+  pdl_prologue();  // (the table above depends on nothing an earlier kernel wrote, so it is built while that one drains)
   if (SHARDED && gather_msg.ch.G > 0) peer_wait(gather_msg.ch, gather_msg.seq);  // the peers' blocks have landed in x_all
   R inv = (R)1;
   const bool rescale = SHARDED && p.x_scale != nullptr;
-  if (rescale) inv = (R)1 / (R)(*p.x_scale);  // exactly the factor k_scale_norm applied to the owner's copy  // pascal[b*33 + c] = C(b, c); the odd stride spreads rows over the banks
-  for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
+  if (rescale) inv = (R)1 / (R)(*p.x_scale);  // exactly the factor k_scale_norm applied to the owner's copy
   __syncthreads();
   const uint32_t lo_mask = (1u << p.half) - 1u;
   const int nbonds = p.periodic ? p.L : p.L - 1;
@@ -277,14 +278,14 @@ template <class T> struct XxzOp : XxzOpBase {
     int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 6));
     if (g < 1) g = 1;
     const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
+    cudaError_t e;
     if (prm.x_all)
-      k_xxz_apply<T, true><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg,
-                                                              cur_gather_msg);
+      e = launch_chain(ctx, k_xxz_apply<T, true>, (int)g, kThreads, 0, (const T*)x, (T*)y, (const uint32_t*)d_states, prm,
+                       (typename Num<T>::R)sigma, pa, msg, cur_gather_msg);
     else
-      k_xxz_apply<T, false><<<(int)g, kThreads, 0, ctx->stream>>>((const T*)x, (T*)y, d_states, prm, (typename Num<T>::R)sigma, pa, msg,
-                                                               PeerMsg());
+      e = launch_chain(ctx, k_xxz_apply<T, false>, (int)g, kThreads, 0, (const T*)x, (T*)y, (const uint32_t*)d_states, prm,
+                       (typename Num<T>::R)sigma, pa, msg, PeerMsg());
     *npa = (int)g;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_apply: %s", cudaGetErrorString(e));
     ctx->launches++;
     return LLZ_OK;
