@@ -409,6 +409,7 @@ int llz_ctx_destroy(llz_ctx_t ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx_trim(ctx);
   comm_destroy(ctx);
+  ctx_trim(ctx);  // the exchange buffers comm_destroy handed back to the pool
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
