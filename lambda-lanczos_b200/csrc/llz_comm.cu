@@ -282,7 +282,7 @@ ExchangeBuffer* comm_exchange_buffer_acquire(llz_ctx_t ctx, size_t bytes) {
   if (!comm_p2p(ctx) || bytes == 0) return nullptr;
   Comm* c = ctx->comm;
   for (ExchangeBuffer* b : c->xbufs)
-    if (!b->in_use && b->bytes == bytes) {
+    if (b->usable && !b->in_use && b->bytes == bytes) {
       b->in_use = true;
       return b;
     }
