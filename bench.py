@@ -2,16 +2,30 @@
 """bench.py — Lanczos iterations/s on BASELINE.json's config 2 (2-D 5-point Laplacian 4096x4096, CSR, double, 4 smallest
 eigenpairs), measured on the GPU(s) and, beside it, on the host CPU with the reference implementation.
 
-A "step" is one complete ``LambdaLanczos::run()`` on that operator with ``max_iteration`` capped (the algorithm stores
-every Lanczos vector — 134 MB each here — so natural convergence, ~16k vectors, fits no machine):
-two Lanczos runs of ``max_iteration`` iterations (the second deflated against the 4 kept vectors) plus eigenvector
-assembly.  value = Lanczos iterations / second over the timed steps.
+A "step" of the GPU arm is one complete ``LambdaLanczos::run()`` on that operator with ``max_iteration`` capped (the
+algorithm stores every Lanczos vector — 134 MB each here — so natural convergence, ~16k vectors, fits no machine;
+SURVEY.md §7.3-3): four Lanczos runs of ``max_iteration`` iterations (runs 2-4 deflated against the 4 kept vectors) plus
+eigenvector assembly and the copy-out of the eigenvectors.  value = Lanczos iterations / second over the timed steps.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Prints ONE JSON line (see the keys below).  ``--impl reference`` times the UNMODIFIED reference (oracle/_ref, compiled
-from /root/reference; falls back to the oracle's C restatement) on the host cores on a bounded sample of the same
-workload.
+Prints ONE JSON line.  Besides the contract's keys it carries
+
+* ``parity``   the GPU path (the very operator storage the bench times, row-sharded when N > 1) against the compiled
+               reference on the same operator and start vector for ``m_ref`` Lanczos iterations: alpha_k, beta_k, every
+               Lanczos vector, the Ritz values.  Outside 1e-10 (north_star tolerance) the bench exits non-zero.
+* ``matched``  both implementations timed on that same capped run (max_iteration = m_ref): like-for-like it/s.
+* ``extra``    the other BASELINE configurations (N = 1: configs 1, 3, 4, 5; N > 1: config 4 at L = 30, row-sharded).
+
+``--impl reference`` times the UNMODIFIED reference (oracle/_ref, compiled from /root/reference) on the host cores on
+the SAME workload.  The reference cannot finish that workload in minutes (an iteration costs 0.5 s + 0.05 s per vector
+it reorthogonalises against; one step is 768 iterations against ~100 vectors on average), so every reference "step" is
+ONE Lanczos iteration of the workload taken at the workload's MEAN reorthogonalisation depth: the reference's public
+``run_iteration(…, orthogonalizeTo)`` is handed a deflation set of q orthonormal vectors so that the timed iterations
+k = W+1 … W+K orthogonalise against k + q vectors with mean(k + q) = the mean of (k + locked) over the GPU arm's step.
+The cost of a reference iteration depends on the operator and on that depth only (util::schmidt_orth is a loop over
+the vectors), so iterations/s of this sample is iterations/s of the workload; what the sample leaves out (the O(k^2)
+tridiagonal QR at k ~ 100, eigenvector assembly) favours the reference.
 """
 from __future__ import annotations
 
@@ -28,13 +42,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this workload
-# at iteration k = 151 (profiles/r01_ncu_full_summary.txt); algorithmic bytes of those launches: 20.67 / 20.53 GB.
-NCU_TRAFFIC = {"project": 20.675e9, "update": 20.363e9}
+# DRAM traffic / algorithmic bytes of the two basis-streaming kernels, from the committed `ncu --set full` captures
+# (dram__bytes_read.sum + dram__bytes_write.sum per launch over the algorithmic bytes of that very launch):
+# profiles/r01b_ncu_full_summary.txt (k = 151, n = 16.7 M): project 20.68 / 20.67 GB, update 20.36 / 20.53 GB;
+# profiles/r02_ncu_traffic_by_k.txt holds the same ratio at other k and at the per-GPU shape of an 8-GPU run.
+NCU_TRAFFIC_RATIO = {"project": 1.000, "update": 0.992}
+NCU_TRAFFIC_SOURCE = "profiles/r01b_ncu_full_summary.txt, profiles/r02_ncu_traffic_by_k.txt"
 
 METRIC = "lanczos_iterations_per_second"
 UNIT = "iterations/s"
+PARITY_TOL = 1e-10      # north_star: eigenvalues within 1e-10 relative (double)
+OVERLAP_TOL = 1e-9      # north_star: |<v_ref, v>| >= 1 - 1e-9
 
 
 def parse_args():
@@ -46,10 +66,12 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=4096, help="grid side of the Laplacian (config 2: 4096)")
     ap.add_argument("--max-iteration", type=int, default=192, help="cap on Lanczos iterations per run (basis must fit HBM)")
     ap.add_argument("--num-eigs", type=int, default=4)
-    ap.add_argument("--cpu-sample-iterations", type=int, default=0, help="max_iteration of the CPU sample (0 = auto)")
+    ap.add_argument("--parity-iterations", type=int, default=16, help="m_ref: iterations of the in-line parity / matched run (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--format", default="sell", choices=["sell", "csr"],
-                    help="device storage of the operator: the user's CSR arrays as they are, or re-stored as SELL-32-sigma")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = --steps)")
+    ap.add_argument("--format", default="auto", choices=["auto", "sell", "csr"],
+                    help="device storage of the operator: auto = what llz_op_create_sell picks for the CSR input")
     return ap.parse_args()
 
 
@@ -113,19 +135,45 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_name(args):
-    return (f"config2: 2-D 5-point Laplacian {args.nx}x{args.nx} (n={args.nx * args.nx}) CSR double, {args.num_eigs} smallest "
-            f"eigenpairs, full reorthogonalisation, max_iteration={args.max_iteration} per Lanczos run")
+def config_dict(args):
+    """The workload, spelled identically by both arms (everything arm-specific lives outside `config`)."""
+    n = args.nx * args.nx
+    return {"workload": (f"config2: 2-D 5-point Laplacian {args.nx}x{args.nx} (n={n}) CSR double, {args.num_eigs} smallest "
+                         f"eigenpairs, full reorthogonalisation, max_iteration={args.max_iteration} per Lanczos run"),
+            "n": n, "nnz": 5 * n - 4 * args.nx, "num_eigs": args.num_eigs, "max_iteration": args.max_iteration,
+            "start_vector": "numpy RandomState(1) uniform[-1,1], the same at the start of every Lanczos run",
+            "l2": f"inputs (Lanczos basis of up to {args.max_iteration + 1} x {n * 8 // 1000000} MB) far exceed the 126 MB L2: no flush needed"}
 
 
-def bytes_model(n, s, a_bytes, counts, num_eigs, nroot=5):
-    """B_run = m*A_bytes + (m(m+1) + (2q+7)m) n s + (m + r) n s, summed over the Lanczos runs."""
-    total = 0.0
-    q = 0
+def workload_depth(max_iteration, num_eigs, counts=None, nroot=5):
+    """Mean number of vectors a Lanczos iteration of the workload reorthogonalises against: k basis vectors plus the
+    locked eigenvectors of the earlier runs.  The capped workload is 4 Lanczos runs of max_iteration iterations with
+    0, 4, 4, 4 locked vectors (what the GPU arm reports as `lanczos_runs_per_step`)."""
+    counts = counts or [max_iteration] * 4
+    tot, its, q = 0.0, 0, 0
     for m in counts:
-        total += m * a_bytes + (m * (m + 1) + (2 * q + 7) * m) * n * s + (m + nroot) * n * s
+        tot += m * (m + 1) / 2.0 + q * m
+        its += m
         q = min(num_eigs, q + nroot)
-    return total
+    return tot / max(its, 1)
+
+
+def depth_blocks(wl, n, q):
+    """q orthonormal vectors with disjoint supports, packed in ONE n-vector: vector j = g restricted to rows
+    [floor(j n / q), floor((j+1) n / q)) (the layout oracle/ref_shim.cpp:run_iteration_spy unpacks)."""
+    g = wl.start_vector(n, seed=9).copy()
+    for j in range(q):
+        lo, hi = j * n // q, (j + 1) * n // q
+        g[lo:hi] /= np.linalg.norm(g[lo:hi])
+    return g
+
+
+def reference_depth_sample(impl, csr, start, g, q, iters, warm, threads):
+    """`iters` timed Lanczos iterations of the reference after `warm` untimed ones, deflating against q vectors."""
+    r = impl.run_iteration(*csr, find_max=False, max_iter=warm + iters + 1, init=start, locked_blocks=g if q > 0 else None,
+                           n_locked=q, mv_threads=threads, want_beta=False)
+    dts = r["dt_iter"][warm:warm + iters]
+    return dts, r
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -133,71 +181,258 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation on the host cores, bounded sample of the workload."""
     if rank != 0:
         return
-    import __graft_entry__ as entry
     import importlib
+
+    import __graft_entry__ as entry
 
     entry.load_package()
     wl = importlib.import_module("lambda_lanczos_b200.workloads")
     import oracle
 
-    impl = oracle.best()
-    threads = impl.host_threads() if hasattr(impl, "host_threads") else 1
+    impl = oracle.best(fast=True)
     n = args.nx * args.nx
     csr = wl.laplacian2d_csr(args.nx)
     start = wl.start_vector(n)
-    kw = dict(find_max=False, num_eigs=args.num_eigs, init=start)
-    if impl.kind == "reference":
-        kw.update(mv_threads=threads, want_vectors=False)
-    m = args.cpu_sample_iterations
-    if m <= 0:
-        # calibrate on a 3-iteration probe: cost ~ c * m^2 per run; keep (steps + warmup) runs within ~150 s
-        t0 = time.perf_counter()
-        impl.lanczos(*csr, max_iter=3, **kw)
-        probe = time.perf_counter() - t0
-        budget = 150.0 / max(1, args.steps + args.warmup)
-        m = int(max(4, min(16, 3 * (budget / max(probe, 1e-3)) ** 0.5)))
-    iters = 0
-    for _ in range(args.warmup):
-        impl.lanczos(*csr, max_iter=m, **kw)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = impl.lanczos(*csr, max_iter=m, **kw)
-        iters += sum(r.iter_counts)
-    dt = time.perf_counter() - t0
-    value = iters / dt
-    sample = (f"same operator and start vector, max_iteration={m} per Lanczos run ({len(r.iter_counts)} runs/step); mv_mul "
-              f"CSR lambda on {threads} thread(s), the reference's vector kernels are single-threaded.  NOTE: the cost of "
-              f"an iteration grows linearly with its index k (full reorthogonalisation against k vectors), so these first "
-              f"{m} iterations are the CHEAPEST of a run: the GPU arm's workload averages k ~ {args.max_iteration // 2}, where "
-              f"a CPU iteration costs ~{max(1, args.max_iteration // (2 * max(m // 2, 1)))}x more than in this sample")
+    K, W = args.steps, args.warmup
+    if impl.kind != "reference":
+        raise SystemExit("oracle/_ref/libllz_ref.so is missing: the reference arm needs the compiled reference "
+                         "(python -c 'import __graft_entry__ as e; e.build()' where /root/reference exists)")
+    threads = impl.host_threads()
+    depth = workload_depth(args.max_iteration, args.num_eigs)
+    q = max(0, int(round(depth - (W + (K + 1) / 2.0))))
+    g = depth_blocks(wl, n, q) if q > 0 else None
+    dts, r = reference_depth_sample(impl, csr, start, g, q, K, W, threads)
+    steps_done = len(dts)
+    total = float(np.sum(dts))
+    value = steps_done / total
+    sample = (f"{steps_done} consecutive Lanczos iterations of the workload (one per step) through the reference's public "
+              f"run_iteration(), after {W} untimed ones, deflated against q={q} orthonormal vectors so that the timed "
+              f"iterations reorthogonalise against k+q = {W + 1 + q}..{W + steps_done + q} vectors (mean "
+              f"{W + (steps_done + 1) / 2.0 + q:.1f}) = the mean depth {depth:.1f} of the workload's {4 * args.max_iteration} "
+              f"iterations; mv_mul = CSR lambda on {threads} OpenMP thread(s), the reference's own vector kernels are "
+              f"single-threaded (all it can use); built {impl.build_flags}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sample": sample},
+            "warmup": args.warmup, "ms_per_step": total / max(steps_done, 1) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": impl.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "details": {"step_definition": "one Lanczos iteration at the workload's mean reorthogonalisation depth",
+                        "seconds_per_iteration": [float(x) for x in dts], "locked_vectors": q, "workload_mean_depth": depth,
+                        "alpha_first": [float(x) for x in r["alpha"][:3]], "build_flags": impl.build_flags},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_baseline(args, wl, csr, start):
+class Group:
+    """torch.distributed plumbing of the GPU arm (NCCL, one process per GPU); everything degenerates for one rank."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+
+        self.torch, self.rank, self.world, self.local_rank = torch, rank, world, local_rank
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self, ctx=None):
+        if ctx is not None:
+            ctx.synchronize()
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, arr):
+        arr = np.asarray(arr, dtype=np.float64)
+        if self.dist is None:
+            return arr
+        t = self.torch.from_numpy(arr.copy()).to(self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def bcast_array(self, arr, shape, dtype=np.float64):
+        """Rank 0's numpy array on every rank (through device memory)."""
+        if self.dist is None:
+            return arr
+        t = (self.torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)) if self.rank == 0 else
+             self.torch.empty(shape, dtype=self.torch.float64)).to(self.dev)
+        self.dist.broadcast(t, src=0)
+        return t.cpu().numpy()
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def parity_and_matched(args, grp, pkg, wl, ctx, op, csr_full_fn, start_full, row0, n_local):
+    """GPU (the operator the bench times, sharded when N > 1) vs the compiled reference, m_ref iterations of the first
+    Lanczos run of the workload: alpha, beta, every Lanczos vector, Ritz values; and both timed on that capped run."""
+    m = args.parity_iterations
+    n = args.nx * args.nx
     import oracle
 
-    impl = oracle.best()
-    threads = impl.host_threads() if hasattr(impl, "host_threads") else 1
-    kw = dict(find_max=False, num_eigs=args.num_eigs, init=start)
-    if impl.kind == "reference":
-        kw.update(mv_threads=threads, want_vectors=False)
-    m = args.cpu_sample_iterations if args.cpu_sample_iterations > 0 else 8
+    ref = None
+    t_ref = {}
+    if grp.rank == 0:
+        strict = oracle.best()           # strict IEEE build: the parity checker
+        if strict.kind != "reference":
+            return {"skipped": "oracle/_ref/libllz_ref.so missing"}, None
+        threads = strict.host_threads()
+        csr = csr_full_fn()
+        ref = strict.run_iteration(*csr, find_max=False, max_iter=m, init=start_full, mv_threads=threads, capture=m)
+        fast = oracle.best(fast=True)    # -O3 build, no spy: the timing leg
+        t0 = time.perf_counter()
+        rr = fast.lanczos(*csr, find_max=False, num_eigs=1, max_iter=m, init=start_full, mv_threads=threads, want_vectors=True)
+        t_ref = {"seconds": time.perf_counter() - t0, "iterations": sum(rr.iter_counts), "threads": threads,
+                 "flags": fast.build_flags, "eigenvalue": float(rr.eigenvalues[0])}
+        del csr
+    # ---- GPU: step-level run for alpha/beta/basis ----
+    kry = pkg.Krylov(ctx, np.float64, n_local, m + 2)
+    kry.set_locked([])
+    kry.begin(np.ascontiguousarray(start_full[row0:row0 + n_local]))
+    ab = []
+    for k in range(1, m + 1):
+        kry.step(op, 0.0, pkg.ORTH_FULL)
+        ab.append(kry.fetch(k))
+    alpha = np.array([a for a, _ in ab])
+    beta = np.array([b for _, b in ab])
+    ref_alpha = grp.bcast_array(ref["alpha"] if ref else None, (m,))
+    ref_beta = grp.bcast_array(ref["beta"] if ref else None, (m - 1,))
+    ref_ritz = grp.bcast_array(ref["eigenvalues"] if ref else None, (min(5, m),))
+    dots = np.zeros(m)
+    diff2 = np.zeros(m)
+    for j in range(m):
+        col_ref = grp.bcast_array(ref["basis"][j] if ref else None, (n,))[row0:row0 + n_local]
+        col = kry.column(j)
+        dots[j] = float(np.dot(col_ref, col))
+        diff2[j] = float(np.sum((col_ref - col) ** 2))
+    dots, diff2 = grp.sum(dots), grp.sum(diff2)
+    kry.close()
+    # Ritz values of T_m from the GPU's alpha/beta (numpy, checker side) and from the engine itself
+    T = np.diag(alpha) + np.diag(beta[:-1], 1) + np.diag(beta[:-1], -1)
+    ritz = np.linalg.eigvalsh(T)[:ref_ritz.size]
+    start_local = np.ascontiguousarray(start_full[row0:row0 + n_local])
+    eng = pkg.LambdaLanczos(op, n, False, 1)
+    eng.init_vector = start_local
+    eng.max_iteration = m
+    ev, vec = eng.run()   # warm-up of the matched timing (maps the basis memory), and the engine's own Ritz value
+    reps = 3
+    grp.barrier(ctx)
     t0 = time.perf_counter()
-    r = impl.lanczos(*csr, max_iter=m, **kw)
-    dt = time.perf_counter() - t0
-    return {"value": sum(r.iter_counts) / dt, "unit": UNIT, "cores": threads, "kind": impl.kind,
-            "sample": f"one run() of the same workload with max_iteration={m} ({sum(r.iter_counts)} iterations, {dt:.1f} s); "
-                      f"mv_mul on {threads} thread(s), reference vector kernels single-threaded; these are the cheapest "
-                      f"iterations of a run (cost grows linearly with the iteration index k; the GPU workload averages "
-                      f"k ~ {args.max_iteration // 2})"}
+    for _ in range(reps):
+        ev, vec = eng.run()
+    grp.barrier(ctx)
+    gpu_s = grp.max(time.perf_counter() - t0) / reps
+    par = {"m_ref": m, "n": n, "operator": "the operator storage the bench times" + (f", row-sharded over {grp.world} GPUs" if grp.world > 1 else ""),
+           "checker": "compiled reference (oracle/_ref/libllz_ref.so, strict IEEE build), run_iteration with an mv_mul spy",
+           "max_rel_alpha": float(np.max(np.abs(alpha - ref_alpha) / np.abs(ref_alpha))),
+           "max_rel_beta": float(np.max(np.abs(beta[:-1] - ref_beta) / np.abs(ref_beta))),
+           "min_overlap": float(np.min(np.abs(dots))), "max_vector_l2_diff": float(np.sqrt(np.max(diff2))),
+           "ritz_rel": float(np.max(np.abs(ritz - ref_ritz) / np.abs(ref_ritz))),
+           "engine_ritz_rel": float(abs(ev[0] - ref_ritz[0]) / abs(ref_ritz[0])),
+           "iterations": {"gpu": eng.getIterationCounts(), "reference": [m]}, "tolerance": PARITY_TOL}
+    par["ok"] = bool(par["max_rel_alpha"] < PARITY_TOL and par["max_rel_beta"] < PARITY_TOL and par["ritz_rel"] < PARITY_TOL and
+                     par["engine_ritz_rel"] < PARITY_TOL and 1.0 - par["min_overlap"] < OVERLAP_TOL)
+    matched = None
+    if grp.rank == 0:
+        matched = {"max_iteration": m, "workload": "one Lanczos run of config 2 capped at m_ref iterations + eigenvector assembly, host vectors out",
+                   "gpu_it_s": m / gpu_s, "gpu_seconds": gpu_s, "ref_it_s": t_ref["iterations"] / t_ref["seconds"],
+                   "ref_seconds": t_ref["seconds"], "ref_threads": t_ref["threads"], "ref_build": t_ref["flags"],
+                   "ratio": (m / gpu_s) / (t_ref["iterations"] / t_ref["seconds"])}
+    return par, matched
+
+
+def cpu_baseline_block(args, grp, pkg, wl, ctx, op, csr_full, start_full, depth):
+    """N = 1 only: the reference on the host cores on a bounded depth-matched sample (see the module docstring), and the
+    GPU on the SAME sample (same operator, start vector, deflation set, iteration count)."""
+    import oracle
+
+    impl = oracle.best(fast=True)
+    if impl.kind != "reference":
+        return None
+    n = args.nx * args.nx
+    threads = impl.host_threads()
+    warm, iters = 1, 3
+    q = max(0, int(round(depth - (warm + (iters + 1) / 2.0))))
+    g = depth_blocks(wl, n, q)
+    t0 = time.perf_counter()
+    dts, r = reference_depth_sample(impl, csr_full, start_full, g, q, iters, warm, threads)
+    cpu_total = time.perf_counter() - t0
+    value = len(dts) / float(np.sum(dts))
+    # the GPU on the same sample, through the step-level C ABI
+    locked = []
+    for j in range(q):
+        lo, hi = j * n // q, (j + 1) * n // q
+        v = np.zeros(n)
+        v[lo:hi] = g[lo:hi]
+        locked.append(pkg.Vector.from_host(ctx, v))
+    kry = pkg.Krylov(ctx, np.float64, n, warm + iters + 3)
+    kry.set_locked(locked)
+    kry.begin(start_full)
+    ab = []
+    ctx.synchronize()
+    for k in range(1, warm + iters + 1):
+        if k == warm + 1:
+            ctx.synchronize()
+            t1 = time.perf_counter()
+        kry.step(op, 0.0, pkg.ORTH_FULL)
+        ab.append(kry.fetch(k))
+    ctx.synchronize()
+    gpu_dt = (time.perf_counter() - t1) / iters
+    alpha = np.array([a for a, _ in ab])
+    rel = float(np.max(np.abs(alpha - r["alpha"][:alpha.size]) / np.abs(alpha)))
+    kry.close()
+    del locked
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": impl.kind,
+            "sample": (f"{len(dts)} Lanczos iterations of the workload through the reference's run_iteration() after {warm} untimed one, "
+                       f"deflated against q={q} orthonormal vectors (reorthogonalisation depth k+q = {warm + 1 + q}..{warm + iters + q}, "
+                       f"the workload's mean is {depth:.1f}); {float(np.sum(dts)):.1f} s timed, {cpu_total:.1f} s in all; mv_mul on "
+                       f"{threads} OpenMP thread(s), reference vector kernels single-threaded; built {impl.build_flags}"),
+            "gpu_same_sample": {"iterations_per_s": 1.0 / gpu_dt, "seconds_per_iteration": gpu_dt,
+                                "alpha_max_rel_diff_vs_reference": rel, "ratio": (1.0 / gpu_dt) / value}}
+
+
+def extra_configs(args, grp, pkg, wl, ctx, peak):
+    """The other BASELINE configurations: N = 1 -> configs 1, 3, 4 (L = 28 to convergence, L = 30 capped),
+    5; N > 1 -> config 4 at L = 30 row-sharded (the 'largest config' of the scaling target)."""
+    import configs as cf
+
+    env = cf.Env(pkg, wl, ctx, grp.rank, grp.world, sync=lambda: grp.barrier(ctx), peak=peak)
+    out = []
+
+    def guarded(fn, *a, **kw):
+        try:
+            ctx.release_cache()
+            d = fn(env, *a, **kw)
+            d.pop("_csr", None)
+            out.append(d)
+        except Exception as e:  # an extra must never cost the headline line
+            out.append({"config": getattr(fn, "__name__", "?"), "error": str(e)[:300]})
+
+    if grp.world == 1:
+        guarded(cf.run_c1)
+        guarded(cf.run_c3)
+        guarded(cf.run_c4, 28, 0)
+        guarded(cf.run_c4, 30, 100)
+        guarded(cf.run_c5, 28, 100)
+    else:
+        guarded(cf.run_c4, 30, 100)
+    ctx.release_cache()
+    return out
 
 
 def run_ours(args, rank, world):
@@ -210,58 +445,62 @@ def run_ours(args, rank, world):
     pkg = entry.load_package()
     wl = importlib.import_module("lambda_lanczos_b200.workloads")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    grp = Group(rank, world, local_rank)
     ctx = pkg.Context(local_rank)
     n = args.nx * args.nx
     if world > 1:
         # row-sharded group: rank 0 makes the communicator id, torch.distributed carries the 128-byte blob
-        blob = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        blob = torch.zeros(128, dtype=torch.uint8, device=grp.dev)
         if rank == 0:
             blob.copy_(torch.frombuffer(bytearray(pkg.Context.unique_id()), dtype=torch.uint8))
-        dist.broadcast(blob, src=0)
+        grp.dist.broadcast(blob, src=0)
         ctx.join(rank, world, bytes(blob.cpu().numpy().tobytes()))
     row0, n_local = wl.partition(n, rank, world)
+
+    def pinned(a):
+        """The same array in page-locked host memory (what the e2e arm copies from / to)."""
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+
+    keep = []
     csr = wl.laplacian2d_csr_rows(args.nx, row0, n_local) if world > 1 else wl.laplacian2d_csr(args.nx)
+    csr_p = []
+    for a in csr:
+        v, t = pinned(a)
+        csr_p.append(v)
+        keep.append(t)
     start_full = wl.start_vector(n)
-    start = np.ascontiguousarray(start_full[row0:row0 + n_local])
+    start, t = pinned(start_full[row0:row0 + n_local])
+    keep.append(t)
+    evec_t = torch.empty((args.num_eigs, n_local), dtype=torch.float64).pin_memory()
+    evec_out = evec_t.numpy()
 
     def make_op():
-        make = pkg.Operator.sell if args.format == "sell" else pkg.Operator.csr
-        return make(ctx, *csr, row0=row0, n_cols=n)
+        if args.format == "csr":
+            return pkg.Operator.csr(ctx, *csr_p, row0=row0, n_cols=n)
+        return pkg.Operator.sell(ctx, *csr_p, row0=row0, n_cols=n)
 
-    def barrier():
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident arm: operator already in HBM, eigenvectors stay on the device ----
     op = make_op()
+    a_bytes = op.bytes()
+    storage = op.storage() if hasattr(op, "storage") else ("CSR" if args.format == "csr" else "SELL-32-sigma")
+
+    # ---- parity + like-for-like timing against the compiled reference, on this very operator ----
+    parity = matched = None
+    if args.parity_iterations > 0:
+        parity, matched = parity_and_matched(args, grp, pkg, wl, ctx, op, lambda: wl.laplacian2d_csr(args.nx), start_full, row0, n_local)
+
+    # ---- device-resident arm: operator already in HBM; eigenvectors copied out to pinned host memory every step ----
     eng = pkg.LambdaLanczos(op, n, False, args.num_eigs)
     eng.init_vector = start
     eng.max_iteration = args.max_iteration
-    eng.want_eigenvectors = False
     for _ in range(args.warmup):
-        eng.run()
-    barrier()
+        eng.run(out=evec_out)
+    grp.barrier(ctx)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.profile(True)
     launches0 = ctx.launch_count()
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))  # the engine's own stream
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=grp.dev)  # the engine's own stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     iters = 0
@@ -269,17 +508,18 @@ def run_ours(args, rank, world):
     host_s = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        evals, _ = eng.run()
+        evals, _ = eng.run(out=evec_out)
         counts = eng.getIterationCounts()
         iters += sum(counts)
         host_s += eng.stats.seconds_host
     ev1.record(stream)
-    barrier()
+    grp.barrier(ctx)
     wall = time.perf_counter() - t0
     # device time of the K steps on the launching stream (host control included), max over the ranks
-    dt = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    dt = grp.max(ev0.elapsed_time(ev1) * 1e-3)
     launches = ctx.launch_count() - launches0
-    prof = {name: ctx.profile_read(name) for name in ("spmv", "halo", "exchange", "project", "reduce", "update", "scale", "combine", "dot")}
+    families = ("spmv", "halo", "exchange", "project", "reduce", "update", "scale", "combine", "dot", "recurrence")
+    prof = {name: ctx.profile_read(name) for name in families}
     ctx.profile(False)
     clocks = sampler.stop()
     value = iters / dt
@@ -290,10 +530,14 @@ def run_ours(args, rank, world):
     ms, cnt, by = prof[dom]
     achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     s = 8
-    a_bytes = op.bytes()
-    model_bytes = bytes_model(n_local, s, a_bytes, counts, args.num_eigs) * args.steps  # per GPU
+    import configs as cf
+
+    model_bytes = cf.lanczos_bytes(counts, n_local, s, a_bytes, args.num_eigs) * args.steps  # per GPU
     roofline = {"bound": "hbm", "kernel": f"k_{dom}<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": NCU_TRAFFIC.get(dom),
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": by / max(cnt, 1) * NCU_TRAFFIC_RATIO[dom], "traffic_over_algorithmic": NCU_TRAFFIC_RATIO[dom],
+                "traffic_source": f"ncu dram bytes / algorithmic bytes of the captured launches ({NCU_TRAFFIC_SOURCE}) x this run's "
+                                  "average algorithmic bytes per launch",
                 "launches": cnt, "avg_launch_ms": ms / max(cnt, 1), "algorithmic_bytes_per_launch": by / max(cnt, 1),
                 "kernel_time_share": {k: v[0] / (dt * 1e3) for k, v in prof.items() if v[1] > 0},
                 "per_kernel_GBps": {k: v[2] / (v[0] * 1e-3) / 1e9 for k, v in prof.items() if v[0] > 0 and v[2] > 0},
@@ -301,47 +545,61 @@ def run_ours(args, rank, world):
                 "whole_step_frac_of_peak": model_bytes / dt / 1e9 / peak,
                 "whole_step_frac_of_nominal_8TBps": model_bytes / dt / 1e9 / 8000.0}
 
-    # ---- end-to-end arm: host CSR arrays in, host eigenvectors out, every step ----
+    # ---- end-to-end arm: pinned host CSR arrays in, host eigenvectors out, every step ----
     del eng, op
-    barrier()
+    grp.barrier(ctx)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else args.steps
     e2e_iters = 0
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 2))
     for _ in range(e2e_steps):
-        op2 = make_op()  # H2D of the operator (this rank's row block)
+        op2 = make_op()  # H2D of the operator (this rank's row block) + device-side re-storage
         eng2 = pkg.LambdaLanczos(op2, n, False, args.num_eigs)
         eng2.init_vector = start
         eng2.max_iteration = args.max_iteration
-        evals2, evecs2 = eng2.run()  # H2D start vector, D2H eigenvectors
+        evals2, evecs2 = eng2.run(out=evec_out)  # H2D start vector, D2H eigenvectors
         e2e_iters += sum(eng2.getIterationCounts())
         del eng2, op2
-    barrier()
-    e2e_dt = max_over_ranks(time.perf_counter() - t0)
+    grp.barrier(ctx)
+    e2e_dt = grp.max(time.perf_counter() - t0)
     h2d = (csr[0].nbytes // 2 + csr[1].nbytes + csr[2].nbytes + start.nbytes) * world  # row pointers travel as int32
-    d2h = evecs2.nbytes * world + 16 * e2e_iters // e2e_steps
+    d2h = evecs2.nbytes * world + 24 * e2e_iters // e2e_steps
     e2e = {"value": e2e_iters / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "seconds_per_step": e2e_dt / e2e_steps}
+           "seconds_per_step": e2e_dt / e2e_steps, "steps": e2e_steps, "host_memory": "pinned"}
 
+    details = {"iterations_per_step": sum(counts), "lanczos_runs_per_step": len(counts),
+               "parallelism": f"rows{world}" if world > 1 else "single GPU",
+               "scalar_exchange": ("peer-memory channels (NVLink stores from the kernels)" if ctx.peer_channels() else "NCCL all-reduce") if world > 1 else None,
+               "operator_storage": f"CSR input re-stored on the device as {storage}", "operator_bytes_per_gpu": int(a_bytes),
+               "value_includes": "eigenvector assembly and the D2H copy of the eigenvectors into pinned host memory",
+               "time_per_step_s": dt / args.steps, "wall_seconds_per_step": wall / args.steps, "host_seconds_per_step": host_s / args.steps,
+               "ritz_values_at_cap": [float(x) for x in evals],
+               "note": "the capped runs do not converge (natural convergence needs ~16k stored vectors): this is a throughput figure; "
+                       "times to a CONVERGED eigenpair are in `extra` (configs 1 and 4)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "iterations_per_step": sum(counts), "lanczos_runs_per_step": len(counts),
-                       "parallelism": f"rows{world}" if world > 1 else "single GPU",
-                       "scalar_exchange": ("peer-memory channels (NVLink stores from the kernels)" if ctx.peer_channels() else "NCCL all-reduce") if world > 1 else None,
-                       "operator_storage": "CSR input re-stored on the device as SELL-32-sigma" if args.format == "sell" else "CSR",
-                       "operator_bytes_per_gpu": int(a_bytes),
-                       "l2": "inputs (basis of up to %d x %d MB per GPU) far exceed the 126 MB L2" % (args.max_iteration + 1, n_local * 8 // 1000000),
-                       "time_to_eigenpair_s": dt / args.steps, "wall_seconds_per_step": wall / args.steps, "host_seconds_per_step": host_s / args.steps,
-                       "eigenvalues": [float(x) for x in evals]},
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args), "details": details,
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if parity is not None:
+        line["parity"] = parity
+    if matched is not None:
+        line["matched"] = matched
+    ctx.release_cache()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(args, wl, csr, start)
+        op3 = make_op()
+        cb = cpu_baseline_block(args, grp, pkg, wl, ctx, op3, csr, start_full, workload_depth(args.max_iteration, args.num_eigs, counts))
+        del op3
+        if cb:
+            line["cpu_baseline"] = cb
+        ctx.release_cache()
+    del csr_p, keep
+    if not args.no_extra:
+        line["extra"] = extra_configs(args, grp, pkg, wl, ctx, peak)
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        ctx.synchronize()
-        dist.barrier()
-        dist.destroy_process_group()
+    grp.barrier(ctx)
+    grp.close()
+    if parity is not None and not parity.get("ok", True) and "skipped" not in parity:
+        sys.exit(3)
 
 
 def main():

@@ -378,7 +378,8 @@ class LambdaLanczos:
         self._iter_counts = []
         self.stats = None
 
-    def run(self):
+    def run(self, out=None):
+        """``out``: optional (num_eigs, n_local) host array receiving the eigenvectors (e.g. a view of pinned memory)."""
         op = self.mv_mul
         n = op.n  # eigenvectors come back as local row blocks
         p = EigsParams(int(self.find_maximum), self.num_eigs, float(self.eigenvalue_offset), float(self.eps),
@@ -387,7 +388,10 @@ class LambdaLanczos:
         start = None if self.init_vector is None else np.ascontiguousarray(self.init_vector, dtype=op.dtype)
         assert start is None or start.size == n, "init_vector must have the operator's (local) row count"
         evals = np.zeros(self.num_eigs, dtype=np.float64)
-        evecs = np.empty((self.num_eigs, n), dtype=op.dtype) if self.want_eigenvectors else None
+        evecs = None
+        if self.want_eigenvectors:
+            evecs = np.empty((self.num_eigs, n), dtype=op.dtype) if out is None else out
+            assert evecs.shape == (self.num_eigs, n) and evecs.dtype == op.dtype and evecs.flags.c_contiguous
         iters = np.zeros(256, dtype=np.int64)
         n_found, n_runs = i64(0), i64(0)
         stats = RunStats()

@@ -113,3 +113,28 @@
 #define T_ABS cabs
 #define T_EXP cexp
 #include "llzo_impl.inc"
+#undef T
+#undef R
+#undef SFX
+#undef RSFX
+#undef CONJ
+#undef RE
+#undef R_EPS
+#undef R_SQRT
+#undef R_ABS
+#undef T_ABS
+#undef T_EXP
+
+/* ---- complex float (the reference template covers it: lambda_lanczos.hpp:109, util/common.hpp:80-102) ---- */
+#define T float _Complex
+#define R float
+#define SFX c64
+#define RSFX f32
+#define CONJ(x) conjf(x)
+#define RE(x) crealf(x)
+#define R_EPS FLT_EPSILON
+#define R_SQRT sqrtf
+#define R_ABS fabsf
+#define T_ABS cabsf
+#define T_EXP cexpf
+#include "llzo_impl.inc"
