@@ -163,9 +163,16 @@ int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* out) {
     }
     ctx->own_stream = true;
   }
-  LLZ_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * kMaxGrid * 2));
-  LLZ_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * 8));
-  LLZ_CUDA(cudaHostAlloc(&ctx->h_result, sizeof(double) * 8, cudaHostAllocDefault));
+  e = cudaMalloc(&ctx->d_partials, sizeof(double) * kMaxGrid * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_result, sizeof(double) * 8);
+  if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_result, sizeof(double) * 8, cudaHostAllocDefault);
+  if (e != cudaSuccess) {  // give back what was created so far
+    if (ctx->d_partials) cudaFree(ctx->d_partials);
+    if (ctx->d_result) cudaFree(ctx->d_result);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "ctx_create: %s", cudaGetErrorString(e));
+  }
   *out = ctx;
   return LLZ_OK;
 }

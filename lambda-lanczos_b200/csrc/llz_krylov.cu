@@ -230,6 +230,8 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
 
 }  // namespace
 
+static int krylov_init(llz_krylov_t kry, int dtype, int64_t n, int64_t max_cols);
+
 extern "C" {
 
 int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz_krylov_t* out) {
@@ -249,9 +251,23 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
     }
     krylov_destroy_now(c);
   }
-  const size_t es = dtype_size(dtype);
   llz_krylov_t kry = new llz_krylov_s();
   kry->ctx = ctx;
+  // every early return below (LLZ_CUDA / fail) must give back the object, its VA reservation and what was allocated
+  const int st = krylov_init(kry, dtype, n, max_cols);
+  if (st != LLZ_OK) {
+    krylov_destroy_now(kry);
+    return st;
+  }
+  *out = kry;
+  return LLZ_OK;
+}
+
+}  // extern "C"
+
+static int krylov_init(llz_krylov_t kry, int dtype, int64_t n, int64_t max_cols) {
+  llz_ctx_t ctx = kry->ctx;
+  const size_t es = dtype_size(dtype);
   kry->requested_cols = max_cols;
   kry->dtype = dtype;
   kry->n = n;
@@ -265,10 +281,7 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
   size_t free_b = 0, total_b = 0;
   LLZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
   int64_t fit = (int64_t)((double)free_b * 0.96 / (double)bytes);
-  if (fit < 2) {
-    delete kry;
-    return fail(LLZ_ERR_OOM, "not even two Lanczos vectors of %zu bytes fit in %zu free bytes", bytes, free_b);
-  }
+  if (fit < 2) return fail(LLZ_ERR_OOM, "not even two Lanczos vectors of %zu bytes fit in %zu free bytes", bytes, free_b);
   kry->cap_cols = std::min<int64_t>(max_cols, fit);
 
   VmmApi& api = vmm();
@@ -297,11 +310,8 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
     // fallback: a single allocation of the whole capacity (bounded so that small problems do not grab the GPU)
     int64_t cols = std::min<int64_t>(kry->cap_cols, std::max<int64_t>(2, (int64_t)(((size_t)8 << 30) / bytes)));
     cudaError_t e = cudaMalloc(&kry->plain, (size_t)cols * bytes);
-    if (e != cudaSuccess) {
-      delete kry;
-      return fail(LLZ_ERR_OOM, "cudaMalloc of the Krylov basis (%lld columns) failed: %s", (long long)cols,
-                  cudaGetErrorString(e));
-    }
+    if (e != cudaSuccess)
+      return fail(LLZ_ERR_OOM, "cudaMalloc of the Krylov basis (%lld columns) failed: %s", (long long)cols, cudaGetErrorString(e));
     kry->cap_cols = cols;
   }
 
@@ -322,14 +332,10 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
   LLZ_CUDA(cudaHostAlloc(&kry->h_wnorm, sc * sizeof(double), cudaHostAllocMapped));
   LLZ_CUDA(cudaHostAlloc(&kry->h_flag, sizeof(long long) * 2, cudaHostAllocMapped));
   kry->h_flag[0] = 0;
-  int s = ensure_cols(kry, 2);
-  if (s != LLZ_OK) {
-    krylov_destroy_now(kry);
-    return s;
-  }
-  *out = kry;
-  return LLZ_OK;
+  return ensure_cols(kry, 2);
 }
+
+extern "C" {
 
 int llz_krylov_destroy(llz_krylov_t kry) {
   if (!kry) return LLZ_OK;
@@ -347,7 +353,7 @@ void llz::krylov_destroy_now(llz_krylov_t kry) {
   if (!kry) return;
   cudaSetDevice(kry->ctx->device);
   cudaStreamSynchronize(kry->ctx->stream);
-  if (kry->use_vmm) {
+  if (kry->use_vmm && kry->va) {
     VmmApi& api = vmm();
     size_t off = 0;
     for (auto h : kry->handles) {
@@ -369,11 +375,8 @@ void llz::krylov_destroy_now(llz_krylov_t kry) {
   if (kry->d_ph) cudaFree(kry->d_ph);
   if (kry->d_ycoef) cudaFree(kry->d_ycoef);
   if (kry->d_qptrs) cudaFree(kry->d_qptrs);
-  cudaFreeHost(kry->h_alpha);
-  cudaFreeHost(kry->h_beta);
-  cudaFreeHost(kry->h_misc);
-  cudaFreeHost(kry->h_wnorm);
-  cudaFreeHost(kry->h_flag);
+  for (void* h : {(void*)kry->h_alpha, (void*)kry->h_beta, (void*)kry->h_misc, (void*)kry->h_wnorm, (void*)kry->h_flag})
+    if (h) cudaFreeHost(h);  // (a workspace whose creation failed half-way holds nulls)
   delete kry;
 }
 

@@ -29,8 +29,11 @@ template <> __device__ __forceinline__ double2 shfl_down_t(double2 v, int o, int
 
 // Column indices of a row-sharded operator use the local "extended" numbering (llz_halo.cpp): [0, nloc) addresses the
 // rank's own block of x, nloc + h the h-th entry of the halo buffer filled by the exchange before the launch.
-template <class T> __device__ __forceinline__ T gather_x(const T* __restrict__ x, const T* __restrict__ halo, int32_t c, int32_t nloc) {
-  return (c < nloc) ? __ldg(x + c) : __ldg(halo + (c - nloc));
+// The halo is written by the PEERS' k_halo_push kernels while this kernel may already be resident (it waits for their
+// announcement in its prologue), so it is not read-only for the kernel's lifetime: it must not go through the
+// non-coherent path (ld.global.nc) — ld.global.cg reads it from L2, where the NVLink stores land.
+template <class T> __device__ __forceinline__ T gather_x(const T* __restrict__ x, const T* halo, int32_t c, int32_t nloc) {
+  return (c < nloc) ? __ldg(x + c) : __ldcg(halo + (c - nloc));
 }
 
 // sendbuf[i] = x[idx[i]]: the entries of the local block the peers asked for, grouped by peer.
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) k_halo_push(const T* __restrict__ x,
 template <class T, class IDX, int LPR>
 __global__ void __launch_bounds__(kThreads, 4)
     k_csr_spmv_dot(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
-                   const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
+                   const T* __restrict__ x, const T* halo, int32_t nloc, T* __restrict__ y, int64_t n,
                    typename Num<T>::R sigma, double* pa, PeerMsg msg, PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
   pdl_prologue();
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 template <class T, class IDX>
 __global__ void __launch_bounds__(kThreads, 4)
     k_csr_stream_dot(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
-                     const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc, T* __restrict__ y, int64_t n,
+                     const T* __restrict__ x, const T* halo, int32_t nloc, T* __restrict__ y, int64_t n,
                      typename Num<T>::R sigma, double* pa, int R, int cap, PeerMsg msg, PeerMsg halo_msg) {
   extern __shared__ __align__(16) unsigned char smem_s[];
   pdl_prologue();
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) k_sell_fill(const IDX* __restrict__ 
 template <class T, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
-                    const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
+                    const int32_t* __restrict__ perm, const T* __restrict__ x, const T* halo, int32_t nloc,
                     T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
                     PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
@@ -329,7 +332,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
 template <class T, int STAGES>
 __global__ void __launch_bounds__(kThreads, 2)
     k_sell_tma_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
-                        const int32_t* __restrict__ perm, const T* __restrict__ x, const T* __restrict__ halo, int32_t nloc,
+                        const int32_t* __restrict__ perm, const T* __restrict__ x, const T* halo, int32_t nloc,
                         T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
                         PeerMsg halo_msg, int cap /* entries per stage */) {
   extern __shared__ __align__(128) unsigned char smem_t[];
