@@ -221,8 +221,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Sum over the CTA; result valid in every thread.  `scratch` needs kWarps doubles.
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
+// Sum over the CTA (NW warps; the streaming kernels all run kWarps); result valid in every thread.  `scratch` needs NW
+// doubles.
+template <int NW = kWarps> __device__ __forceinline__ double block_sum(double v, double* scratch) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();  // protect scratch from a previous use
@@ -230,7 +231,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   __syncthreads();
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) t += scratch[w];
+  for (int w = 0; w < NW; ++w) t += scratch[w];
   return t;
 }
 
@@ -249,6 +250,7 @@ __device__ __forceinline__ double block_sum_partials(const double* __restrict__ 
 // `push` (optional): the kernel also stored its output vector into the peers' exchange buffers (fused all-gather);
 // the last CTA announces that message too.  (The callers' block_sum barrier orders every thread's stores before thread
 // 0's fence, which is cumulative.)
+template <int NW = kWarps>
 __device__ __forceinline__ void finish_scalar(double cta_value, double* partials, const PeerMsg& msg, double* scratch,
                                               const GatherPush* push = nullptr) {
   if (threadIdx.x == 0) partials[blockIdx.x] = cta_value;
@@ -268,8 +270,8 @@ __device__ __forceinline__ void finish_scalar(double cta_value, double* partials
   if (!last_cta) return;
   __threadfence();
   double v = 0.0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v += __ldcg(partials + i);
-  v = block_sum(v, scratch);
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += NW * 32) v += __ldcg(partials + i);
+  v = block_sum<NW>(v, scratch);
   if ((int)threadIdx.x < msg.ch.G) {
     peer_slot(msg.ch, threadIdx.x, msg.seq, msg.ch.rank)[0] = v;
     __threadfence_system();

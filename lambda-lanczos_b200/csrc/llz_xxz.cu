@@ -163,6 +163,215 @@ __global__ void __launch_bounds__(kThreads, 6)
   finish_scalar(t, pa, msg, scratch);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Block kernel (the default).  Split a basis state into its m low bits and its high bits, s = (h << m) | l.  The states
+// that share h are CONSECUTIVE rows — a block of C(m, p) rows, p = n_up - popcount(h), starting at row base(h) — and
+// inside a block the row index is the rank of l among the m-bit strings of popcount p, whatever h is.  Hence
+//   * a bond inside the low bits maps a block onto itself, and the row it leads to depends on (p, l) only: the CTA
+//     stages the block's x segment in shared memory (one contiguous read) and follows per-(p, l) neighbour lists it
+//     built once per popcount class — 13 of the ~28 bonds never leave shared memory;
+//   * a bond inside the high bits maps the whole block onto another block with the same l's: x[base(h') + i], a
+//     contiguous, perfectly coalesced stream whose offset is uniform over the CTA;
+//   * only the bond across the split (bits m-1 | m) and the periodic wrap bond (bits L-1 | 0) gather individually.
+// Nothing per state is stored: no state table, no rank table — A_bytes is a few hundred KB of popcount-class tables.
+// CTAs take the blocks in the order of a host-built list (grouped by popcount class, so the neighbour lists are
+// rebuilt ~m times per launch, and so that the blocks in flight are each other's high-bond neighbours in L2).
+// Products are added in bond order 0, 1, ..., L-2, wrap — the order of the plain per-state loop (k_xxz_apply), so
+// both kernels produce the same bits, and a row-sharded run the same bits as a single GPU.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kXxzMaxLow = 14;       // 16-bit neighbour offsets: C(14,7) * 16 B < 65536
+constexpr int kXxzHighPrefetch = 4;  // high-bond loads issued per state before the shared-memory gathers
+
+struct XxzBlockParams {
+  int L, n_up, m, periodic;
+  double jz4, jxy2;
+  const uint16_t* t_lo;   // [2^m]     row of a low configuration inside its block
+  const uint16_t* t_ls;   // [2^m]     low configurations grouped by popcount: t_ls[ls_off[p] + i]
+  const uint32_t* t_hi;   // [2^(L-m)] first row of the block of a high configuration
+  const uint2* blocks;    // [nblocks] (h, base(h)) of the blocks that intersect the local rows
+  int nblocks;
+  int bsmax;              // rows of the largest block
+  int ls_off[kXxzMaxLow + 2];
+  int32_t n, row0;        // local rows [row0, row0 + n)
+  const void* x_all;      // row-sharded: the whole input vector (see XxzParams)
+  const double* x_scale;
+};
+
+struct XxzBlockDesc {
+  int32_t base, bs, i0, i1;  // first row, rows, local row range [i0, i1) of the block
+  int32_t p;                 // popcount of the low part
+  int32_t nhigh;             // anti-parallel bonds inside the high bits
+  int32_t h0;                // bit 0 of h, or -1 when there is no bond across the split
+  int32_t top;               // bit L-1 when it lies in h (else -1: read it from l), for the wrap bond
+  int32_t wrap_base;         // base(h ^ top bit)
+  int32_t delta[32];         // row offsets of the high bonds (ascending bond order)
+};
+
+template <class T, bool SHARDED>
+__device__ __forceinline__ T xxz_load(const T* __restrict__ x, const T* xg, int32_t g, int32_t row0, int32_t n, bool rescale,
+                                      typename Num<T>::R inv) {
+  if (!SHARDED) return __ldg(x + g);
+  const int32_t j = g - row0;
+  if ((uint32_t)j < (uint32_t)n) return __ldg(x + j);
+  T v = __ldcg(xg + g);  // written by peers while this kernel may be resident: not through the non-coherent path
+  return rescale ? scale_real(v, inv) : v;
+}
+
+template <class T, bool SHARDED, int NT>
+__global__ void __launch_bounds__(NT)
+    k_xxz_block_apply(const T* __restrict__ x, T* __restrict__ y, XxzBlockParams p, typename Num<T>::R sigma, double* pa,
+                      PeerMsg msg, PeerMsg gather_msg) {
+  using R = typename Num<T>::R;
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_x[];
+  __shared__ double scratch[NW];
+  __shared__ uint32_t pascal[32 * 33];
+  __shared__ XxzBlockDesc desc[2];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 32 * 32; i += NT) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
+  pdl_prologue();
+  // shared memory: x tile (+ zero slot) | neighbour offsets [m-1][bsmax] | meta [bsmax] | low states [bsmax]
+  const int bsmax = p.bsmax;
+  T* xs = reinterpret_cast<T*>(smem_x);
+  uint16_t* nb = reinterpret_cast<uint16_t*>(smem_x + (((size_t)bsmax + 1) * sizeof(T) + 15) / 16 * 16);
+  uint16_t* mt = nb + (size_t)(p.m > 1 ? p.m - 1 : 0) * bsmax;
+  uint16_t* ls = mt + bsmax;
+  if (SHARDED && gather_msg.ch.G > 0) peer_wait(gather_msg.ch, gather_msg.seq);
+  R inv = (R)1;
+  const bool rescale = SHARDED && p.x_scale != nullptr;
+  if (rescale) inv = (R)1 / (R)(*p.x_scale);
+  const T* xg = reinterpret_cast<const T*>(p.x_all);
+  const int m = p.m, L = p.L;
+  const int nhb = L - m - 1;  // bonds inside the high bits
+  const int nbonds = p.periodic ? L : L - 1;
+  const bool wrap_in_low = L - 1 < m;
+  const uint32_t wrap_lmask = 1u | (wrap_in_low ? (1u << (L - 1)) : 0u);
+  __syncthreads();
+
+  // warp 0: the descriptor of work item `it` of this CTA
+  auto describe = [&](int it, XxzBlockDesc& d) {
+    const int lane = tid;
+    const uint2 blk = __ldg(p.blocks + it);
+    const uint32_t h = blk.x;
+    const int pp = p.n_up - __popc(h);
+    bool anti = false;
+    int32_t dl = 0;
+    if (lane < nhb) {
+      anti = (((h >> lane) ^ (h >> (lane + 1))) & 1u) != 0;
+      const int c = pp + __popc(h & ((1u << lane) - 1u));
+      const int32_t dd = (int32_t)pascal[(m + lane) * 33 + c];
+      dl = ((h >> lane) & 1u) ? dd : -dd;
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, anti);
+    if (anti) d.delta[__popc(mask & ((1u << lane) - 1u))] = dl;
+    if (lane == 0) {
+      const int32_t base = (int32_t)blk.y, bs = (int32_t)pascal[m * 33 + pp];
+      d.base = base;
+      d.bs = bs;
+      d.p = pp;
+      d.i0 = max(0, p.row0 - base);
+      d.i1 = min(bs, p.row0 + p.n - base);
+      d.nhigh = __popc(mask);
+      d.h0 = (L > m) ? (int32_t)(h & 1u) : -1;
+      d.top = wrap_in_low ? -1 : (int32_t)((h >> (L - 1 - m)) & 1u);
+      d.wrap_base = (p.periodic && !wrap_in_low) ? (int32_t)__ldg(p.t_hi + (h ^ (1u << (L - 1 - m)))) : 0;
+    }
+  };
+
+  int it = blockIdx.x;
+  if (it < p.nblocks && tid < 32) describe(it, desc[0]);
+  __syncthreads();
+  int cur_p = -1, buf = 0;
+  double dot = 0.0;
+  for (; it < p.nblocks; it += gridDim.x, buf ^= 1) {
+    const XxzBlockDesc& d = desc[buf];
+    const int32_t base = d.base, bs = d.bs, i0 = d.i0, i1 = d.i1;
+    // ---- the x segment of the block (and the zero the padding entries of the neighbour lists point at) ----
+    for (int i = tid; i < bs; i += NT) xs[i] = xxz_load<T, SHARDED>(x, xg, base + i, p.row0, p.n, rescale, inv);
+    if (tid == 0) xs[bs] = zero_of(T());
+    // ---- neighbour lists of this popcount class (the previous block's readers passed the barrier below) ----
+    if (d.p != cur_p) {
+      cur_p = d.p;
+      const uint16_t* lsp = p.t_ls + p.ls_off[cur_p];
+      const uint32_t zero_slot = (uint32_t)bs * (uint32_t)sizeof(T);
+      for (int i = tid; i < bs; i += NT) {
+        const uint32_t l = __ldg(lsp + i);
+        int c = 0, anti = 0;
+        for (int b = 0; b + 1 < m; ++b) {
+          const uint32_t up = (l >> b) & 1u;
+          uint32_t off = zero_slot;
+          if (((l >> (b + 1)) & 1u) != up) {
+            const int32_t dd = (int32_t)pascal[b * 33 + c];
+            off = (uint32_t)(up ? i + dd : i - dd) * (uint32_t)sizeof(T);
+            ++anti;
+          }
+          nb[(size_t)b * bsmax + i] = (uint16_t)off;
+          c += (int)up;
+        }
+        // bond across the split: rank distance C(m-1, c), direction from bit m-1 (meaningful only when m >= 1)
+        const uint32_t dsplit = m >= 1 ? pascal[(m - 1) * 33 + c] : 0u;
+        const uint32_t upm = m >= 1 ? (l >> (m - 1)) & 1u : 0u;
+        mt[i] = (uint16_t)(dsplit | (upm << 11) | ((uint32_t)anti << 12));
+        ls[i] = (uint16_t)l;
+      }
+    }
+    if (tid < 32 && it + (int)gridDim.x < p.nblocks) describe(it + gridDim.x, desc[buf ^ 1]);
+    __syncthreads();
+    // ---- one row per thread ----
+    const int nhigh = d.nhigh;
+    for (int i = i0 + tid; i < i1; i += NT) {
+      const int32_t g = base + i;
+      const uint32_t meta = mt[i];
+      // global gathers first (their latency overlaps the shared-memory part)
+      const uint32_t upm = (meta >> 11) & 1u;
+      const bool split = d.h0 >= 0 && (int32_t)upm != d.h0;
+      T vsplit = zero_of(T());
+      if (split) {
+        const int32_t dd = (int32_t)(meta & 0x7ffu);
+        vsplit = xxz_load<T, SHARDED>(x, xg, upm ? g + dd : g - dd, p.row0, p.n, rescale, inv);
+      }
+      T hv[kXxzHighPrefetch];
+#pragma unroll
+      for (int u = 0; u < kXxzHighPrefetch; ++u)
+        hv[u] = u < nhigh ? xxz_load<T, SHARDED>(x, xg, g + d.delta[u], p.row0, p.n, rescale, inv) : zero_of(T());
+      bool wrap = false;
+      T vwrap = zero_of(T());
+      if (p.periodic) {
+        const uint32_t l = ls[i];
+        const uint32_t topbit = wrap_in_low ? (l >> (L - 1)) & 1u : (uint32_t)d.top;
+        wrap = (l & 1u) != topbit;
+        if (wrap) vwrap = xxz_load<T, SHARDED>(x, xg, d.wrap_base + (int32_t)__ldg(p.t_lo + (l ^ wrap_lmask)), p.row0, p.n, rescale, inv);
+      }
+      T acc = zero_of(T());
+      const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs);
+#pragma unroll 4
+      for (int b = 0; b + 1 < m; ++b) acc = add_t(acc, *reinterpret_cast<const T*>(xb + nb[(size_t)b * bsmax + i]));
+      acc = add_t(acc, vsplit);
+#pragma unroll
+      for (int u = 0; u < kXxzHighPrefetch; ++u) acc = add_t(acc, hv[u]);
+      for (int k0 = kXxzHighPrefetch; k0 < nhigh; k0 += kXxzHighPrefetch) {
+#pragma unroll
+        for (int u = 0; u < kXxzHighPrefetch; ++u)
+          hv[u] = k0 + u < nhigh ? xxz_load<T, SHARDED>(x, xg, g + d.delta[k0 + u], p.row0, p.n, rescale, inv) : zero_of(T());
+#pragma unroll
+        for (int u = 0; u < kXxzHighPrefetch; ++u) acc = add_t(acc, hv[u]);
+      }
+      acc = add_t(acc, vwrap);
+      const int anti = (int)(meta >> 12) + (split ? 1 : 0) + nhigh + (wrap ? 1 : 0);
+      const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
+      const T xi = xs[i];
+      T yi = scale_real(acc, (R)p.jxy2);
+      yi = add_t(yi, scale_real(xi, diag + sigma));
+      y[g - p.row0] = yi;
+      dot += re_conj_mul(xi, yi);
+    }
+    __syncthreads();  // the tile, the lists and desc[buf] are free again
+  }
+  const double t = block_sum<NW>(dot, scratch);
+  finish_scalar<NW>(t, pa, msg, scratch);
+}
+
 // Which entries of the input vector does this row block read from every other rank?  Per owner the smallest and the
 // largest global index (same target arithmetic as k_xxz_apply), so that only those ranges travel: with 8 ranks a block
 // reads 13-38 % of the vector, not the 87.5 % a plain all-gather moves.
@@ -217,7 +426,17 @@ struct XxzOpBase : OpBase {
   XxzParams prm;
   uint32_t* d_lo = nullptr;
   uint32_t* d_hi = nullptr;
-  uint32_t* d_states = nullptr;  // basis states of the local block
+  uint32_t* d_states = nullptr;  // basis states of the local block (per-state kernel and set-up only)
+  // block kernel: popcount-class tables and the block list
+  bool per_state = false;  // LLZ_XXZ_KERNEL=state: the plain one-thread-per-state kernel (kept as the A/B reference)
+  XxzBlockParams bp;
+  uint16_t* d_tlo = nullptr;
+  uint16_t* d_tls = nullptr;
+  uint32_t* d_thi = nullptr;
+  uint2* d_blocks = nullptr;
+  int block_threads = 256;
+  size_t block_smem = 0;
+  int block_grid = 1;
   void* d_xall = nullptr;  // row-sharded runs: gathered input vector (n_global elements), NCCL path
   std::vector<size_t> send_off, send_bytes, recv_off, recv_bytes;
   // fused all-gather: a double-buffered (by message parity) whole-vector buffer on every rank, mapped into every peer
@@ -229,8 +448,13 @@ struct XxzOpBase : OpBase {
     if (d_hi) dev_free(ctx, d_hi);
     if (d_xall) dev_free(ctx, d_xall);
     if (d_states) dev_free(ctx, d_states);
+    if (d_tlo) dev_free(ctx, d_tlo);
+    if (d_tls) dev_free(ctx, d_tls);
+    if (d_thi) dev_free(ctx, d_thi);
+    if (d_blocks) dev_free(ctx, d_blocks);
     if (xb) comm_exchange_buffer_release(ctx, xb);
   }
+  virtual int plan_block_kernel() = 0;
   size_t vec_bytes() const { return ((size_t)n_global * dtype_size(dtype) + 255) / 256 * 256; }  // stride between the two copies
   bool plan_push(GatherPush* push) override {
     if (!xb) return false;
@@ -273,12 +497,52 @@ struct XxzOpBase : OpBase {
 };
 
 template <class T> struct XxzOp : XxzOpBase {
+  template <int NT> static size_t configure(size_t smem, int* per_sm) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_xxz_block_apply<T, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_xxz_block_apply<T, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_xxz_block_apply<T, false, NT>, NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_xxz_block_apply<T, true, NT>, NT, smem);
+    *per_sm = std::max(1, std::min(a, b));
+    return smem;
+  }
+  // shared memory of the block kernel and the persistent grid that keeps every SM full
+  int plan_block_kernel() override {
+    const size_t tile = (((size_t)bp.bsmax + 1) * sizeof(T) + 15) / 16 * 16;
+    block_smem = tile + (size_t)(std::max(bp.m - 1, 0) + 2) * bp.bsmax * sizeof(uint16_t);
+    if (block_smem > 200 * 1024) return fail(LLZ_ERR_INVALID, "op_create_xxz: %d low bits need %zu bytes of shared memory", bp.m, block_smem);
+    int per_sm = 1;
+    if (block_threads == 512)
+      configure<512>(block_smem, &per_sm);
+    else
+      configure<256>(block_smem, &per_sm);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "op_create_xxz: block kernel set-up: %s", cudaGetErrorString(e));
+    block_grid = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)bp.nblocks, (int64_t)kMaxGrid, (int64_t)ctx->num_sms * per_sm}));
+    return LLZ_OK;
+  }
+  template <int NT> cudaError_t launch_block(const void* x, void* y, double sigma, double* pa, const PeerMsg& msg) {
+    bp.x_all = prm.x_all;
+    bp.x_scale = prm.x_scale;
+    if (prm.x_all)
+      return launch_chain(ctx, k_xxz_block_apply<T, true, NT>, block_grid, NT, block_smem, (const T*)x, (T*)y, bp, (typename Num<T>::R)sigma,
+                          pa, msg, cur_gather_msg);
+    return launch_chain(ctx, k_xxz_block_apply<T, false, NT>, block_grid, NT, block_smem, (const T*)x, (T*)y, bp, (typename Num<T>::R)sigma,
+                        pa, msg, PeerMsg());
+  }
   int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg* alpha_msg) override {
+    const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
+    cudaError_t e;
+    if (!per_state) {
+      e = block_threads == 512 ? launch_block<512>(x, y, sigma, pa, msg) : launch_block<256>(x, y, sigma, pa, msg);
+      *npa = block_grid;
+      if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_block_apply: %s", cudaGetErrorString(e));
+      ctx->launches++;
+      return LLZ_OK;
+    }
     // persistent: exactly the 6 CTAs per SM that __launch_bounds__(kThreads, 6) keeps resident
     int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 6));
     if (g < 1) g = 1;
-    const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
-    cudaError_t e;
     if (prm.x_all)
       e = launch_chain(ctx, k_xxz_apply<T, true>, (int)g, kThreads, 0, (const T*)x, (T*)y, (const uint32_t*)d_states, prm,
                        (typename Num<T>::R)sigma, pa, msg, cur_gather_msg);
@@ -302,6 +566,88 @@ static void init_binom() {
     for (int k = 1; k <= n; ++k) host_binom[n][k] = host_binom[n - 1][k - 1] + (k <= n - 1 ? host_binom[n - 1][k] : 0);
   }
   binom_ready = true;
+}
+
+// Low bits of the split used by the block kernel: 13 (blocks of up to 1716 rows, ~60 KB of shared memory per CTA) once
+// the sector is large; fewer for short chains so that there are enough blocks to spread over the SMs.
+static int xxz_low_bits(int L) {
+  int m = std::min(L, std::max(6, std::min(13, L - 10)));
+  if (const char* env = getenv("LLZ_XXZ_M")) {
+    const int v = atoi(env);
+    if (v >= 1) m = std::min({v, L, kXxzMaxLow});
+  }
+  return m;
+}
+
+// Popcount-class tables and the block list of the block kernel (host, O(2^m + 2^(L-m))).
+static int build_block_tables(XxzOpBase* op, int L, int n_up) {
+  llz_ctx_t ctx = op->ctx;
+  const int m = xxz_low_bits(L);
+  const int hb = L - m;
+  XxzBlockParams& bp = op->bp;
+  bp.L = L;
+  bp.n_up = n_up;
+  bp.m = m;
+  bp.periodic = op->prm.periodic;
+  bp.jz4 = op->prm.jz4;
+  bp.jxy2 = op->prm.jxy2;
+  bp.n = (int32_t)op->n_local;
+  bp.row0 = (int32_t)op->row0;
+  bp.x_all = nullptr;
+  bp.x_scale = nullptr;
+  std::vector<uint16_t> tlo((size_t)1 << m), tls((size_t)1 << m);
+  bp.ls_off[0] = 0;
+  for (int pp = 0; pp <= m; ++pp) bp.ls_off[pp + 1] = bp.ls_off[pp] + (int)host_binom[m][pp];
+  for (uint32_t l = 0; l < tlo.size(); ++l) {
+    unsigned long long r = 0;
+    int j = 0;
+    for (int q = 0; q < m; ++q)
+      if (l >> q & 1u) r += host_binom[q][++j];
+    tlo[l] = (uint16_t)r;
+    tls[(size_t)bp.ls_off[j] + r] = (uint16_t)l;
+  }
+  std::vector<uint32_t> thi((size_t)1 << hb, 0u);
+  // blocks that intersect the local rows, by popcount class; classes in order of decreasing block size
+  std::vector<std::vector<uint2>> by_class((size_t)m + 1);
+  int bsmax = 1;
+  for (uint32_t h = 0; h < thi.size(); ++h) {
+    const int pp = n_up - __builtin_popcount(h);
+    if (pp < 0 || pp > m) continue;
+    unsigned long long r = 0;
+    int j = pp;
+    for (int q = 0; q < hb; ++q)
+      if (h >> q & 1u) r += host_binom[q + m][++j];
+    thi[h] = (uint32_t)r;
+    const int64_t bs = (int64_t)host_binom[m][pp];
+    if ((int64_t)r < op->row0 + op->n_local && (int64_t)r + bs > op->row0) {
+      by_class[(size_t)pp].push_back(make_uint2(h, (uint32_t)r));
+      bsmax = std::max(bsmax, (int)bs);
+    }
+  }
+  std::vector<int> order;
+  for (int pp = 0; pp <= m; ++pp) order.push_back(pp);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return host_binom[m][a] > host_binom[m][b]; });
+  std::vector<uint2> blocks;
+  for (int pp : order) blocks.insert(blocks.end(), by_class[(size_t)pp].begin(), by_class[(size_t)pp].end());
+  if (blocks.empty()) return fail(LLZ_ERR_INVALID, "op_create_xxz: no basis state in the local row block");
+  bp.nblocks = (int)blocks.size();
+  bp.bsmax = (bsmax + 1) & ~1;
+  cudaError_t e = dev_malloc(ctx, &op->d_tlo, tlo.size() * sizeof(uint16_t));
+  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_tls, tls.size() * sizeof(uint16_t));
+  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_thi, thi.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_blocks, blocks.size() * sizeof(uint2));
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_tlo, tlo.data(), tlo.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_tls, tls.data(), tls.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_thi, thi.data(), thi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_blocks, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "op_create_xxz: block tables: %s", cudaGetErrorString(e));
+  bp.t_lo = op->d_tlo;
+  bp.t_ls = op->d_tls;
+  bp.t_hi = op->d_thi;
+  bp.blocks = op->d_blocks;
+  op->bytes = (int64_t)(tlo.size() + tls.size()) * 2 + (int64_t)thi.size() * 4 + (int64_t)blocks.size() * 8;
+  if (const char* env = getenv("LLZ_XXZ_THREADS")) op->block_threads = atoi(env) == 512 ? 512 : 256;
+  return op->plan_block_kernel();
 }
 
 }  // namespace llz
@@ -374,13 +720,28 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
   op->prm.row0 = op->row0;
   op->prm.x_all = nullptr;
   op->prm.x_scale = nullptr;
-  op->bytes = op->n_local * 4;  // the state table is the only stored part of the operator
-  e = dev_malloc(ctx, &op->d_states, sizeof(uint32_t) * (size_t)op->n_local);
-  if (e != cudaSuccess) {
-    delete op;
-    return fail(LLZ_ERR_OOM, "op_create_xxz: state table (%lld entries): %s", (long long)op->n_local, cudaGetErrorString(e));
-  }
   {
+    const char* env = getenv("LLZ_XXZ_KERNEL");
+    op->per_state = env && env[0] == 's';
+  }
+  if (!op->per_state) {
+    const int st = build_block_tables(op, L, n_up);
+    if (st != LLZ_OK) {
+      delete op;
+      return st;
+    }
+  } else {
+    op->bytes = op->n_local * 4;  // the state table is the only stored part of the operator
+  }
+  // the state table: what the per-state kernel reads, and what the row-sharded set-up derives its index ranges from
+  if (op->per_state || ctx->nranks > 1) {
+    e = dev_malloc(ctx, &op->d_states, sizeof(uint32_t) * (size_t)op->n_local);
+    if (e != cudaSuccess) {
+      delete op;
+      return fail(LLZ_ERR_OOM, "op_create_xxz: state table (%lld entries): %s", (long long)op->n_local, cudaGetErrorString(e));
+    }
+  }
+  if (op->d_states) {
     const int64_t nchunks = (op->n_local + 31) / 32;
     const int grid = (int)std::min<int64_t>((nchunks + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 8);
     k_xxz_states<<<std::max(grid, 1), kThreads, 0, ctx->stream>>>(op->d_states, op->n_local, op->row0, L, n_up);
@@ -467,6 +828,10 @@ extern "C" int llz_op_create_xxz(llz_ctx_t ctx, int dtype, int L, int n_up, doub
       op->send_off[r] = (size_t)(lo - op->row0) * es;
       op->send_bytes[r] = (size_t)(hi - lo) * es;
     }
+  }
+  if (!op->per_state && op->d_states) {  // only the set-up needed it
+    dev_free(ctx, op->d_states);
+    op->d_states = nullptr;
   }
   llz_op_t h = new llz_op_s();
   h->impl = op;

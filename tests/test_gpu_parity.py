@@ -214,7 +214,30 @@ def test_xxz_matrix_free_matches_explicit_matrix(pkg, ctx, wl, L, n_up, pbc, dty
     assert op.n == n == math.comb(L, n_up)
     x = rnd(np.random.RandomState(L), n, dtype)
     assert np.allclose(op.matvec(x), wl.csr_matvec(*csr, x), rtol=1e-13, atol=1e-13)
-    assert op.bytes() == 4 * op.n  # the state table is all the operator stores
+    assert op.bytes() < 64 * 1024 + 12 * 2 ** max(L - 6, 0)  # popcount-class tables and a block list: nothing per state
+
+
+@pytest.mark.parametrize("L,n_up,pbc", [(2, 1, True), (3, 1, True), (5, 2, False), (9, 4, True), (12, 6, True), (15, 7, False),
+                                        (18, 9, True), (20, 10, True), (20, 4, True), (17, 15, True), (6, 0, True), (6, 6, True)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+def test_xxz_block_kernel_is_bit_identical_to_per_state_kernel(pkg, ctx, wl, monkeypatch, L, n_up, pbc, dtype):
+    """The block kernel (low-bit bonds through shared-memory neighbour lists, high-bit bonds as contiguous streams) adds
+    the products of a row in the same bond order as the plain one-thread-per-state kernel: same bits, for every split of
+    the bit string (no high bits at all, one high bit, the default, the largest supported low part)."""
+    n = math.comb(L, n_up)
+    x = rnd(np.random.RandomState(7 * L + n_up), n, dtype)
+    monkeypatch.setenv("LLZ_XXZ_KERNEL", "state")
+    y_ref = pkg.Operator.xxz(ctx, L, n_up, jz=0.7, jxy=1.3, periodic=pbc, dtype=dtype).matvec(x)
+    monkeypatch.delenv("LLZ_XXZ_KERNEL")
+    for m in sorted({0, L, L - 1, 1, 2, min(L, 14), max(1, L // 2)}):
+        if m == 0:
+            monkeypatch.delenv("LLZ_XXZ_M", raising=False)  # the default split
+        else:
+            monkeypatch.setenv("LLZ_XXZ_M", str(m))
+        for threads in ("256", "512"):
+            monkeypatch.setenv("LLZ_XXZ_THREADS", threads)
+            y = pkg.Operator.xxz(ctx, L, n_up, jz=0.7, jxy=1.3, periodic=pbc, dtype=dtype).matvec(x)
+            assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), (m, threads, np.abs(y - y_ref).max())
 
 
 # ---- the Lanczos recurrence itself: alpha, beta and the basis, iteration by iteration -------------------------------
