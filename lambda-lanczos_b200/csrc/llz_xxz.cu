@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "llz_device.cuh"
@@ -65,6 +66,17 @@ __global__ void __launch_bounds__(kThreads) k_xxz_states(uint32_t* __restrict__ 
       s = gosper_next(s);
     }
   }
+}
+
+// y_r = Jxy/2 * (sum of the flipped neighbours) + (diag + sigma) * x_r with a fixed rounding sequence (product, then one
+// fused multiply-add), so that the per-state and the block kernel — and every instantiation of them — agree bit for bit.
+__device__ __forceinline__ float xxz_row(float acc, float xi, float jxy2, float dg) { return fmaf(xi, dg, __fmul_rn(acc, jxy2)); }
+__device__ __forceinline__ double xxz_row(double acc, double xi, double jxy2, double dg) { return fma(xi, dg, __dmul_rn(acc, jxy2)); }
+__device__ __forceinline__ float2 xxz_row(float2 acc, float2 xi, float jxy2, float dg) {
+  return make_float2(xxz_row(acc.x, xi.x, jxy2, dg), xxz_row(acc.y, xi.y, jxy2, dg));
+}
+__device__ __forceinline__ double2 xxz_row(double2 acc, double2 xi, double jxy2, double dg) {
+  return make_double2(xxz_row(acc.x, xi.x, jxy2, dg), xxz_row(acc.y, xi.y, jxy2, dg));
 }
 
 // One thread per basis state, consecutive threads on consecutive states, and a loop over the BONDS that is uniform
@@ -154,8 +166,7 @@ __global__ void __launch_bounds__(kThreads, 6)
     }
     const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
     const T xi = x[r];
-    T yi = scale_real(acc, (R)p.jxy2);
-    yi = add_t(yi, scale_real(xi, diag + sigma));
+    const T yi = xxz_row(acc, xi, (R)p.jxy2, diag + sigma);
     y[r] = yi;
     dot += re_conj_mul(xi, yi);
   }
@@ -180,16 +191,14 @@ __global__ void __launch_bounds__(kThreads, 6)
 // Products are added in bond order 0, 1, ..., L-2, wrap — the order of the plain per-state loop (k_xxz_apply), so
 // both kernels produce the same bits, and a row-sharded run the same bits as a single GPU.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kXxzMaxLow = 14;       // 16-bit neighbour offsets: C(14,7) * 16 B < 65536
-constexpr int kXxzHighPrefetch = 4;  // high-bond loads issued per state before the shared-memory gathers
+constexpr int kXxzMaxLow = 13;       // blocks of at most C(13,6) = 1716 rows: <= 7 rows per thread of a 256-thread CTA
 
 struct XxzBlockParams {
   int L, n_up, m, periodic;
   double jz4, jxy2;
   const uint16_t* t_lo;   // [2^m]     row of a low configuration inside its block
   const uint16_t* t_ls;   // [2^m]     low configurations grouped by popcount: t_ls[ls_off[p] + i]
-  const uint32_t* t_hi;   // [2^(L-m)] first row of the block of a high configuration
-  const uint2* blocks;    // [nblocks] (h, base(h)) of the blocks that intersect the local rows
+  const uint4* blocks;    // [nblocks] (h, base(h), base(h ^ top bit), 0) of the blocks that intersect the local rows
   int nblocks;
   int bsmax;              // rows of the largest block
   int ls_off[kXxzMaxLow + 2];
@@ -205,7 +214,8 @@ struct XxzBlockDesc {
   int32_t h0;                // bit 0 of h, or -1 when there is no bond across the split
   int32_t top;               // bit L-1 when it lies in h (else -1: read it from l), for the wrap bond
   int32_t wrap_base;         // base(h ^ top bit)
-  int32_t delta[32];         // row offsets of the high bonds (ascending bond order)
+  int32_t mode[32];          // per high bond: 0 = the neighbour block is local, 1 = remote (gathered vector), 2 = both
+  const void* src[32];       // per high bond (ascending bond order): address of row 0 of the neighbour block's x segment
 };
 
 template <class T, bool SHARDED>
@@ -218,43 +228,64 @@ __device__ __forceinline__ T xxz_load(const T* __restrict__ x, const T* xg, int3
   return rescale ? scale_real(v, inv) : v;
 }
 
-template <class T, bool SHARDED, int NT>
-__global__ void __launch_bounds__(NT)
+// cp.async of one element (4, 8 or 16 bytes) into shared memory
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+
+// resident CTAs the register allocation must allow: 4 of 256 threads (64 registers) unless the loads a thread keeps in
+// flight alone need more
+template <class T, int NT, int R, int D> constexpr int xxz_min_blocks() {
+  return (int)sizeof(T) * R * D <= 64 ? 1024 / NT : 512 / NT;
+}
+
+template <class T, bool SHARDED, int NT, int R, int D>
+__global__ void __launch_bounds__(NT, xxz_min_blocks<T, NT, R, D>())
     k_xxz_block_apply(const T* __restrict__ x, T* __restrict__ y, XxzBlockParams p, typename Num<T>::R sigma, double* pa,
                       PeerMsg msg, PeerMsg gather_msg) {
-  using R = typename Num<T>::R;
+  using RT = typename Num<T>::R;
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_x[];
   __shared__ double scratch[NW];
   __shared__ uint32_t pascal[32 * 33];
-  __shared__ XxzBlockDesc desc[2];
+  __shared__ XxzBlockDesc desc[3];  // block it % 3: written one block ahead, while the slowest warp may still read it - 1
   const int tid = threadIdx.x;
   for (int i = tid; i < 32 * 32; i += NT) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
   pdl_prologue();
-  // shared memory: x tile (+ zero slot) | neighbour offsets [m-1][bsmax] | meta [bsmax] | low states [bsmax]
+  // shared memory: two x tiles of bsmax + 1 elements (the last one is the zero the padding entries of the neighbour
+  // lists point at) | neighbour offsets [bsmax][E] (E = m - 1 rounded up to 4: a row's list is E/4 8-byte loads) |
+  // meta [bsmax] | low states [bsmax]
   const int bsmax = p.bsmax;
-  T* xs = reinterpret_cast<T*>(smem_x);
-  uint16_t* nb = reinterpret_cast<uint16_t*>(smem_x + (((size_t)bsmax + 1) * sizeof(T) + 15) / 16 * 16);
-  uint16_t* mt = nb + (size_t)(p.m > 1 ? p.m - 1 : 0) * bsmax;
-  uint16_t* ls = mt + bsmax;
-  if (SHARDED && gather_msg.ch.G > 0) peer_wait(gather_msg.ch, gather_msg.seq);
-  R inv = (R)1;
-  const bool rescale = SHARDED && p.x_scale != nullptr;
-  if (rescale) inv = (R)1 / (R)(*p.x_scale);
-  const T* xg = reinterpret_cast<const T*>(p.x_all);
   const int m = p.m, L = p.L;
+  const int E4 = (m - 1 + 3) / 4;  // 8-byte words of neighbour offsets per row
+  const size_t tile_bytes = (((size_t)bsmax + 1) * sizeof(T) + 15) / 16 * 16;
+  uint2* nb = reinterpret_cast<uint2*>(smem_x + 2 * tile_bytes);
+  uint16_t* mt = reinterpret_cast<uint16_t*>(nb + (size_t)E4 * bsmax);
+  uint16_t* ls = mt + bsmax;
+  if (tid < 2) reinterpret_cast<T*>(smem_x + tid * tile_bytes)[bsmax] = zero_of(T());
+  if (SHARDED && gather_msg.ch.G > 0) peer_wait(gather_msg.ch, gather_msg.seq);
+  RT inv = (RT)1;
+  const bool rescale = SHARDED && p.x_scale != nullptr;
+  if (rescale) inv = (RT)1 / (RT)(*p.x_scale);
+  const T* xg = reinterpret_cast<const T*>(p.x_all);
   const int nhb = L - m - 1;  // bonds inside the high bits
   const int nbonds = p.periodic ? L : L - 1;
   const bool wrap_in_low = L - 1 < m;
   const uint32_t wrap_lmask = 1u | (wrap_in_low ? (1u << (L - 1)) : 0u);
   __syncthreads();
+  auto load = [&](int32_t g) -> T { return xxz_load<T, SHARDED>(x, xg, g, p.row0, p.n, rescale, inv); };
 
-  // warp 0: the descriptor of work item `it` of this CTA
-  auto describe = [&](int it, XxzBlockDesc& d) {
+  // warp 0: the descriptor of a work item from its block-list entry (shared-memory look-ups only: the entry itself was
+  // fetched an iteration earlier, so nothing here waits for global memory)
+  auto describe = [&](const uint4 blk, XxzBlockDesc& d) {
     const int lane = tid;
-    const uint2 blk = __ldg(p.blocks + it);
     const uint32_t h = blk.x;
     const int pp = p.n_up - __popc(h);
+    const int32_t base = (int32_t)blk.y, bs = (int32_t)pascal[m * 33 + pp];
     bool anti = false;
     int32_t dl = 0;
     if (lane < nhb) {
@@ -264,9 +295,15 @@ __global__ void __launch_bounds__(NT)
       dl = ((h >> lane) & 1u) ? dd : -dd;
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, anti);
-    if (anti) d.delta[__popc(mask & ((1u << lane) - 1u))] = dl;
+    if (anti) {
+      const int k = __popc(mask & ((1u << lane) - 1u));
+      const int32_t g0 = base + dl;  // the neighbour block: rows [g0, g0 + bs)
+      int mode = 0;
+      if (SHARDED) mode = (g0 >= p.row0 && g0 + bs <= p.row0 + p.n) ? 0 : ((g0 + bs <= p.row0 || g0 >= p.row0 + p.n) ? 1 : 2);
+      d.mode[k] = mode;
+      d.src[k] = mode == 1 ? (const void*)(xg + g0) : (const void*)(x + (g0 - p.row0));
+    }
     if (lane == 0) {
-      const int32_t base = (int32_t)blk.y, bs = (int32_t)pascal[m * 33 + pp];
       d.base = base;
       d.bs = bs;
       d.p = pp;
@@ -275,98 +312,197 @@ __global__ void __launch_bounds__(NT)
       d.nhigh = __popc(mask);
       d.h0 = (L > m) ? (int32_t)(h & 1u) : -1;
       d.top = wrap_in_low ? -1 : (int32_t)((h >> (L - 1 - m)) & 1u);
-      d.wrap_base = (p.periodic && !wrap_in_low) ? (int32_t)__ldg(p.t_hi + (h ^ (1u << (L - 1 - m)))) : 0;
+      d.wrap_base = (int32_t)blk.z;
     }
+  };
+  // asynchronous copy of a block's x segment into tile `buf`.  Row-sharded: a block that straddles the boundary of the
+  // local rows is staged through registers instead (its remote entries come from the gathered vector, re-scaled).
+  auto stage = [&](const XxzBlockDesc& d, int buf) {
+    T* xs = reinterpret_cast<T*>(smem_x + buf * tile_bytes);
+    if (SHARDED && (d.i0 > 0 || d.i1 < d.bs)) {
+      for (int i = tid; i < d.bs; i += NT) xs[i] = load(d.base + i);
+    } else {
+      const T* src = x + (d.base - p.row0);
+      for (int i = tid; i < d.bs; i += NT) cp_async_elem<(int)sizeof(T)>(xs + i, src + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // element `i` of the x segment of the neighbour block of high bond k
+  auto high = [&](const XxzBlockDesc& d, int k, uint32_t i) -> T {
+    const T* src = reinterpret_cast<const T*>(d.src[k]);
+    if (!SHARDED) return __ldg(src + i);
+    const int mode = d.mode[k];
+    if (mode == 0) return __ldg(src + i);
+    if (mode == 1) {
+      const T v = __ldcg(src + i);
+      return rescale ? scale_real(v, inv) : v;
+    }
+    return load((int32_t)(src - x) + p.row0 + (int32_t)i);
   };
 
   int it = blockIdx.x;
-  if (it < p.nblocks && tid < 32) describe(it, desc[0]);
+  const int stride = (int)gridDim.x;
+  uint4 entry = make_uint4(0u, 0u, 0u, 0u);  // warp 0: the block-list entry of the block after the next one
+  if (tid < 32) {
+    if (it < p.nblocks) describe(__ldg(p.blocks + it), desc[0]);
+    if (it + stride < p.nblocks) entry = __ldg(p.blocks + it + stride);
+  }
   __syncthreads();
-  int cur_p = -1, buf = 0;
+  if (it < p.nblocks) stage(desc[0], 0);
+  int cur_p = -1, buf = 0, ds = 0;
   double dot = 0.0;
-  for (; it < p.nblocks; it += gridDim.x, buf ^= 1) {
-    const XxzBlockDesc& d = desc[buf];
-    const int32_t base = d.base, bs = d.bs, i0 = d.i0, i1 = d.i1;
-    // ---- the x segment of the block (and the zero the padding entries of the neighbour lists point at) ----
-    for (int i = tid; i < bs; i += NT) xs[i] = xxz_load<T, SHARDED>(x, xg, base + i, p.row0, p.n, rescale, inv);
-    if (tid == 0) xs[bs] = zero_of(T());
-    // ---- neighbour lists of this popcount class (the previous block's readers passed the barrier below) ----
+  for (; it < p.nblocks; it += stride, buf ^= 1, ds = ds == 2 ? 0 : ds + 1) {
+    const XxzBlockDesc& d = desc[ds];
+    XxzBlockDesc& dnext = desc[ds == 2 ? 0 : ds + 1];
+    const bool more = it + stride < p.nblocks;
+    if (tid < 32 && more) {
+      describe(entry, dnext);
+      if (it + 2 * stride < p.nblocks) entry = __ldg(p.blocks + it + 2 * stride);
+    }
+    // ---- neighbour lists of this popcount class ----
     if (d.p != cur_p) {
+      __syncthreads();  // the previous block's readers of the lists are done
       cur_p = d.p;
+      const int32_t bs = d.bs;
       const uint16_t* lsp = p.t_ls + p.ls_off[cur_p];
-      const uint32_t zero_slot = (uint32_t)bs * (uint32_t)sizeof(T);
+      const uint32_t zero_slot = (uint32_t)bsmax * (uint32_t)sizeof(T);
+      uint16_t* nb16 = reinterpret_cast<uint16_t*>(nb);
       for (int i = tid; i < bs; i += NT) {
         const uint32_t l = __ldg(lsp + i);
         int c = 0, anti = 0;
-        for (int b = 0; b + 1 < m; ++b) {
+        uint16_t* row = nb16 + (size_t)i * (4 * E4);
+        for (int b = 0; b < 4 * E4; ++b) {
           const uint32_t up = (l >> b) & 1u;
           uint32_t off = zero_slot;
-          if (((l >> (b + 1)) & 1u) != up) {
-            const int32_t dd = (int32_t)pascal[b * 33 + c];
-            off = (uint32_t)(up ? i + dd : i - dd) * (uint32_t)sizeof(T);
-            ++anti;
+          if (b + 1 < m) {
+            if (((l >> (b + 1)) & 1u) != up) {
+              const int32_t dd = (int32_t)pascal[b * 33 + c];
+              off = (uint32_t)(up ? i + dd : i - dd) * (uint32_t)sizeof(T);
+              ++anti;
+            }
+            c += (int)up;
           }
-          nb[(size_t)b * bsmax + i] = (uint16_t)off;
-          c += (int)up;
+          row[b] = (uint16_t)off;
         }
-        // bond across the split: rank distance C(m-1, c), direction from bit m-1 (meaningful only when m >= 1)
-        const uint32_t dsplit = m >= 1 ? pascal[(m - 1) * 33 + c] : 0u;
-        const uint32_t upm = m >= 1 ? (l >> (m - 1)) & 1u : 0u;
+        // bond across the split: rank distance C(m-1, c), direction from bit m-1
+        const uint32_t dsplit = pascal[(m - 1) * 33 + c];
+        const uint32_t upm = (l >> (m - 1)) & 1u;
         mt[i] = (uint16_t)(dsplit | (upm << 11) | ((uint32_t)anti << 12));
         ls[i] = (uint16_t)l;
       }
     }
-    if (tid < 32 && it + (int)gridDim.x < p.nblocks) describe(it + gridDim.x, desc[buf ^ 1]);
-    __syncthreads();
-    // ---- one row per thread ----
+    const int32_t base = d.base, i0 = d.i0, i1 = d.i1;
     const int nhigh = d.nhigh;
-    for (int i = i0 + tid; i < i1; i += NT) {
-      const int32_t g = base + i;
-      const uint32_t meta = mt[i];
-      // global gathers first (their latency overlaps the shared-memory part)
-      const uint32_t upm = (meta >> 11) & 1u;
-      const bool split = d.h0 >= 0 && (int32_t)upm != d.h0;
-      T vsplit = zero_of(T());
-      if (split) {
-        const int32_t dd = (int32_t)(meta & 0x7ffu);
-        vsplit = xxz_load<T, SHARDED>(x, xg, upm ? g + dd : g - dd, p.row0, p.n, rescale, inv);
-      }
-      T hv[kXxzHighPrefetch];
+    // ---- R rows per thread and pass, bond-major: the loads of a bond are independent across the rows, only the
+    //      additions of a row form a chain (in bond order); D bonds' worth of loads stay in flight, the first D of a
+    //      pass are issued before the previous pass is finished (for the first pass: before the tile barrier).  A warp
+    //      whose rows all lie beyond the block skips the pass. ----
+    uint32_t ir[R];
+    bool act[R];
+    T hv[D][R];
+    auto begin_pass = [&](int32_t ib) {
 #pragma unroll
-      for (int u = 0; u < kXxzHighPrefetch; ++u)
-        hv[u] = u < nhigh ? xxz_load<T, SHARDED>(x, xg, g + d.delta[u], p.row0, p.n, rescale, inv) : zero_of(T());
-      bool wrap = false;
-      T vwrap = zero_of(T());
+      for (int r = 0; r < R; ++r) {
+        const int32_t i = ib + r * NT;
+        act[r] = i < i1;
+        ir[r] = (uint32_t)(act[r] ? i : i1 - 1);  // rows beyond the block repeat its last row (and store nothing)
+      }
+#pragma unroll
+      for (int u = 0; u < D; ++u) {
+        if (u < nhigh) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) hv[u][r] = high(d, u, ir[r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) hv[u][r] = zero_of(T());
+        }
+      }
+    };
+    int32_t ib = i0 + tid;
+    if (ib - (tid & 31) < i1) begin_pass(ib);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile `buf` has landed; every thread is done with the previous block, i.e. with tile buf ^ 1
+    if (more) stage(dnext, buf ^ 1);  // the next block's segment travels while this one is computed
+    const T* xs = reinterpret_cast<const T*>(smem_x + buf * tile_bytes);
+    const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs);
+    T* yb = y + (base - p.row0);
+    while (ib - (tid & 31) < i1) {
+      uint32_t meta[R];
+      T vsplit[R], vwrap[R];
+      int extra[R];  // anti-parallel bonds of the row beyond the low and the high ones
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        meta[r] = mt[ir[r]];
+        const uint32_t upm = (meta[r] >> 11) & 1u;
+        const bool split = d.h0 >= 0 && (int32_t)upm != d.h0;
+        const int32_t dd = (int32_t)(meta[r] & 0x7ffu);
+        vsplit[r] = split ? load(base + (int32_t)ir[r] + (upm ? dd : -dd)) : zero_of(T());
+        extra[r] = split ? 1 : 0;
+        vwrap[r] = zero_of(T());
+      }
       if (p.periodic) {
-        const uint32_t l = ls[i];
-        const uint32_t topbit = wrap_in_low ? (l >> (L - 1)) & 1u : (uint32_t)d.top;
-        wrap = (l & 1u) != topbit;
-        if (wrap) vwrap = xxz_load<T, SHARDED>(x, xg, d.wrap_base + (int32_t)__ldg(p.t_lo + (l ^ wrap_lmask)), p.row0, p.n, rescale, inv);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint32_t l = ls[ir[r]];
+          const uint32_t topbit = wrap_in_low ? (l >> (L - 1)) & 1u : (uint32_t)d.top;
+          const bool wrap = (l & 1u) != topbit;
+          if (wrap) vwrap[r] = load(d.wrap_base + (int32_t)__ldg(p.t_lo + (l ^ wrap_lmask)));
+          extra[r] += wrap ? 1 : 0;
+        }
       }
-      T acc = zero_of(T());
-      const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs);
-#pragma unroll 4
-      for (int b = 0; b + 1 < m; ++b) acc = add_t(acc, *reinterpret_cast<const T*>(xb + nb[(size_t)b * bsmax + i]));
-      acc = add_t(acc, vsplit);
+      T acc[R];
 #pragma unroll
-      for (int u = 0; u < kXxzHighPrefetch; ++u) acc = add_t(acc, hv[u]);
-      for (int k0 = kXxzHighPrefetch; k0 < nhigh; k0 += kXxzHighPrefetch) {
+      for (int r = 0; r < R; ++r) acc[r] = zero_of(T());
+      for (int e = 0; e < E4; ++e) {
+        uint2 q[R];
 #pragma unroll
-        for (int u = 0; u < kXxzHighPrefetch; ++u)
-          hv[u] = k0 + u < nhigh ? xxz_load<T, SHARDED>(x, xg, g + d.delta[k0 + u], p.row0, p.n, rescale, inv) : zero_of(T());
+        for (int r = 0; r < R; ++r) q[r] = nb[(size_t)ir[r] * E4 + e];
 #pragma unroll
-        for (int u = 0; u < kXxzHighPrefetch; ++u) acc = add_t(acc, hv[u]);
+        for (int r = 0; r < R; ++r) {
+          const T v0 = *reinterpret_cast<const T*>(xb + (q[r].x & 0xffffu)), v1 = *reinterpret_cast<const T*>(xb + (q[r].x >> 16));
+          const T v2 = *reinterpret_cast<const T*>(xb + (q[r].y & 0xffffu)), v3 = *reinterpret_cast<const T*>(xb + (q[r].y >> 16));
+          acc[r] = add_t(add_t(add_t(add_t(acc[r], v0), v1), v2), v3);
+        }
       }
-      acc = add_t(acc, vwrap);
-      const int anti = (int)(meta >> 12) + (split ? 1 : 0) + nhigh + (wrap ? 1 : 0);
-      const R diag = (R)(p.jz4 * (double)(nbonds - 2 * anti));
-      const T xi = xs[i];
-      T yi = scale_real(acc, (R)p.jxy2);
-      yi = add_t(yi, scale_real(xi, diag + sigma));
-      y[g - p.row0] = yi;
-      dot += re_conj_mul(xi, yi);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = add_t(acc[r], vsplit[r]);
+      for (int k0 = 0; k0 < nhigh; k0 += D) {
+#pragma unroll
+        for (int u = 0; u < D; ++u) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = add_t(acc[r], hv[u][r]);
+          if (k0 + u + D < nhigh) {  // refill the slot just consumed
+#pragma unroll
+            for (int r = 0; r < R; ++r) hv[u][r] = high(d, k0 + u + D, ir[r]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) hv[u][r] = zero_of(T());
+          }
+        }
+      }
+      // this pass's rows, then the next pass's first loads (while the results below are formed and stored)
+      uint32_t irow[R];
+      bool arow[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        irow[r] = ir[r];
+        arow[r] = act[r];
+      }
+      ib += NT * R;
+      if (ib - (tid & 31) < i1) begin_pass(ib);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (arow[r]) {
+          const T a = add_t(acc[r], vwrap[r]);
+          const int anti = (int)(meta[r] >> 12) + nhigh + extra[r];
+          const RT diag = (RT)(p.jz4 * (double)(nbonds - 2 * anti));
+          const T xi = xs[irow[r]];
+          const T yi = xxz_row(a, xi, (RT)p.jxy2, diag + sigma);
+          yb[irow[r]] = yi;
+          dot += re_conj_mul(xi, yi);
+        }
+      }
     }
-    __syncthreads();  // the tile, the lists and desc[buf] are free again
   }
   const double t = block_sum<NW>(dot, scratch);
   finish_scalar<NW>(t, pa, msg, scratch);
@@ -432,9 +568,7 @@ struct XxzOpBase : OpBase {
   XxzBlockParams bp;
   uint16_t* d_tlo = nullptr;
   uint16_t* d_tls = nullptr;
-  uint32_t* d_thi = nullptr;
-  uint2* d_blocks = nullptr;
-  int block_threads = 256;
+  uint4* d_blocks = nullptr;
   size_t block_smem = 0;
   int block_grid = 1;
   void* d_xall = nullptr;  // row-sharded runs: gathered input vector (n_global elements), NCCL path
@@ -450,7 +584,6 @@ struct XxzOpBase : OpBase {
     if (d_states) dev_free(ctx, d_states);
     if (d_tlo) dev_free(ctx, d_tlo);
     if (d_tls) dev_free(ctx, d_tls);
-    if (d_thi) dev_free(ctx, d_thi);
     if (d_blocks) dev_free(ctx, d_blocks);
     if (xb) comm_exchange_buffer_release(ctx, xb);
   }
@@ -497,46 +630,58 @@ struct XxzOpBase : OpBase {
 };
 
 template <class T> struct XxzOp : XxzOpBase {
-  template <int NT> static size_t configure(size_t smem, int* per_sm) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_xxz_block_apply<T, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_xxz_block_apply<T, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int a = 0, b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_xxz_block_apply<T, false, NT>, NT, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_xxz_block_apply<T, true, NT>, NT, smem);
-    *per_sm = std::max(1, std::min(a, b));
-    return smem;
+  // threads per CTA, rows per thread and pass, high bonds in flight: measured best of {1,2,4} x {2,4,8} rows x bonds and
+  // 256/512 threads on L = 28 for double and complex<double> (tools/bench_xxz.py, profiles/r02_xxz_block_kernel.md)
+  template <class F> int dispatch(F&& f) {
+    using std::integral_constant;
+    return f(integral_constant<int, 256>(), integral_constant<int, 2>(), integral_constant<int, 4>());
   }
   // shared memory of the block kernel and the persistent grid that keeps every SM full
   int plan_block_kernel() override {
-    const size_t tile = (((size_t)bp.bsmax + 1) * sizeof(T) + 15) / 16 * 16;
-    block_smem = tile + (size_t)(std::max(bp.m - 1, 0) + 2) * bp.bsmax * sizeof(uint16_t);
+    const size_t tile = (((size_t)bp.bsmax + 1) * sizeof(T) + 15) / 16 * 16;  // two of them: the next block's segment is prefetched
+    block_smem = 2 * tile + (size_t)((bp.m - 1 + 3) / 4 * 4 + 2) * bp.bsmax * sizeof(uint16_t);
     if (block_smem > 200 * 1024) return fail(LLZ_ERR_INVALID, "op_create_xxz: %d low bits need %zu bytes of shared memory", bp.m, block_smem);
     int per_sm = 1;
-    if (block_threads == 512)
-      configure<512>(block_smem, &per_sm);
-    else
-      configure<256>(block_smem, &per_sm);
+    const size_t smem = block_smem;
+    LLZ_TRY(dispatch([&](auto nt, auto r, auto dd) {
+      constexpr int NT = decltype(nt)::value, RR = decltype(r)::value, DD = decltype(dd)::value;
+      if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(k_xxz_block_apply<T, false, NT, RR, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_xxz_block_apply<T, true, NT, RR, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      }
+      int a = 0, b = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_xxz_block_apply<T, false, NT, RR, DD>, NT, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_xxz_block_apply<T, true, NT, RR, DD>, NT, smem);
+      per_sm = std::max(1, std::min(a, b));
+      return (int)LLZ_OK;
+    }));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "op_create_xxz: block kernel set-up: %s", cudaGetErrorString(e));
     block_grid = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)bp.nblocks, (int64_t)kMaxGrid, (int64_t)ctx->num_sms * per_sm}));
     return LLZ_OK;
   }
-  template <int NT> cudaError_t launch_block(const void* x, void* y, double sigma, double* pa, const PeerMsg& msg) {
+  int launch_block(const void* x, void* y, double sigma, double* pa, const PeerMsg& msg) {
     bp.x_all = prm.x_all;
     bp.x_scale = prm.x_scale;
-    if (prm.x_all)
-      return launch_chain(ctx, k_xxz_block_apply<T, true, NT>, block_grid, NT, block_smem, (const T*)x, (T*)y, bp, (typename Num<T>::R)sigma,
-                          pa, msg, cur_gather_msg);
-    return launch_chain(ctx, k_xxz_block_apply<T, false, NT>, block_grid, NT, block_smem, (const T*)x, (T*)y, bp, (typename Num<T>::R)sigma,
-                        pa, msg, PeerMsg());
+    return dispatch([&](auto nt, auto r, auto dd) {
+      constexpr int NT = decltype(nt)::value, RR = decltype(r)::value, DD = decltype(dd)::value;
+      cudaError_t e;
+      if (prm.x_all)
+        e = launch_chain(ctx, k_xxz_block_apply<T, true, NT, RR, DD>, block_grid, NT, block_smem, (const T*)x, (T*)y, bp,
+                         (typename Num<T>::R)sigma, pa, msg, cur_gather_msg);
+      else
+        e = launch_chain(ctx, k_xxz_block_apply<T, false, NT, RR, DD>, block_grid, NT, block_smem, (const T*)x, (T*)y, bp,
+                         (typename Num<T>::R)sigma, pa, msg, PeerMsg());
+      if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_block_apply: %s", cudaGetErrorString(e));
+      return (int)LLZ_OK;
+    });
   }
   int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg* alpha_msg) override {
     const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
     cudaError_t e;
     if (!per_state) {
-      e = block_threads == 512 ? launch_block<512>(x, y, sigma, pa, msg) : launch_block<256>(x, y, sigma, pa, msg);
+      LLZ_TRY(launch_block(x, y, sigma, pa, msg));
       *npa = block_grid;
-      if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_xxz_block_apply: %s", cudaGetErrorString(e));
       ctx->launches++;
       return LLZ_OK;
     }
@@ -568,10 +713,11 @@ static void init_binom() {
   binom_ready = true;
 }
 
-// Low bits of the split used by the block kernel: 13 (blocks of up to 1716 rows, ~60 KB of shared memory per CTA) once
-// the sector is large; fewer for short chains so that there are enough blocks to spread over the SMs.
+// Low bits of the split used by the block kernel: 12 (blocks of up to 924 rows, ~40 KB of shared memory per CTA: four
+// resident CTAs; measured best on L = 28, 11 and 13 are ~20 % slower) once the sector is large; fewer for short chains
+// so that there are enough blocks to spread over the SMs.  LLZ_XXZ_M overrides (tests cover every split).
 static int xxz_low_bits(int L) {
-  int m = std::min(L, std::max(6, std::min(13, L - 10)));
+  int m = std::min(L, std::max(6, std::min(12, L - 10)));
   if (const char* env = getenv("LLZ_XXZ_M")) {
     const int v = atoi(env);
     if (v >= 1) m = std::min({v, L, kXxzMaxLow});
@@ -608,7 +754,7 @@ static int build_block_tables(XxzOpBase* op, int L, int n_up) {
   }
   std::vector<uint32_t> thi((size_t)1 << hb, 0u);
   // blocks that intersect the local rows, by popcount class; classes in order of decreasing block size
-  std::vector<std::vector<uint2>> by_class((size_t)m + 1);
+  std::vector<std::vector<uint4>> by_class((size_t)m + 1);
   int bsmax = 1;
   for (uint32_t h = 0; h < thi.size(); ++h) {
     const int pp = n_up - __builtin_popcount(h);
@@ -620,33 +766,31 @@ static int build_block_tables(XxzOpBase* op, int L, int n_up) {
     thi[h] = (uint32_t)r;
     const int64_t bs = (int64_t)host_binom[m][pp];
     if ((int64_t)r < op->row0 + op->n_local && (int64_t)r + bs > op->row0) {
-      by_class[(size_t)pp].push_back(make_uint2(h, (uint32_t)r));
+      by_class[(size_t)pp].push_back(make_uint4(h, (uint32_t)r, 0u, 0u));
       bsmax = std::max(bsmax, (int)bs);
     }
   }
   std::vector<int> order;
   for (int pp = 0; pp <= m; ++pp) order.push_back(pp);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return host_binom[m][a] > host_binom[m][b]; });
-  std::vector<uint2> blocks;
+  std::vector<uint4> blocks;
   for (int pp : order) blocks.insert(blocks.end(), by_class[(size_t)pp].begin(), by_class[(size_t)pp].end());
+  if (L - 1 >= m)  // the wrap bond toggles bit L-1, which lies in the high part: first row of the block it leads to
+    for (uint4& b : blocks) b.z = thi[b.x ^ (1u << (L - 1 - m))];
   if (blocks.empty()) return fail(LLZ_ERR_INVALID, "op_create_xxz: no basis state in the local row block");
   bp.nblocks = (int)blocks.size();
   bp.bsmax = (bsmax + 1) & ~1;
   cudaError_t e = dev_malloc(ctx, &op->d_tlo, tlo.size() * sizeof(uint16_t));
   if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_tls, tls.size() * sizeof(uint16_t));
-  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_thi, thi.size() * sizeof(uint32_t));
-  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_blocks, blocks.size() * sizeof(uint2));
+  if (e == cudaSuccess) e = dev_malloc(ctx, &op->d_blocks, blocks.size() * sizeof(uint4));
   if (e == cudaSuccess) e = cudaMemcpy(op->d_tlo, tlo.data(), tlo.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(op->d_tls, tls.data(), tls.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(op->d_thi, thi.data(), thi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(op->d_blocks, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_blocks, blocks.data(), blocks.size() * sizeof(uint4), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LLZ_ERR_OOM : LLZ_ERR_CUDA, "op_create_xxz: block tables: %s", cudaGetErrorString(e));
   bp.t_lo = op->d_tlo;
   bp.t_ls = op->d_tls;
-  bp.t_hi = op->d_thi;
   bp.blocks = op->d_blocks;
-  op->bytes = (int64_t)(tlo.size() + tls.size()) * 2 + (int64_t)thi.size() * 4 + (int64_t)blocks.size() * 8;
-  if (const char* env = getenv("LLZ_XXZ_THREADS")) op->block_threads = atoi(env) == 512 ? 512 : 256;
+  op->bytes = (int64_t)(tlo.size() + tls.size()) * 2 + (int64_t)blocks.size() * 16;
   return op->plan_block_kernel();
 }
 

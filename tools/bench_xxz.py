@@ -1,5 +1,5 @@
 """XXZ apply micro-benchmark on the GPU box: the block kernel under several splits / CTA sizes and the per-state kernel.
-    python tools/bench_xxz.py L [variants...]     variant = kernel[:m[:threads]], e.g. block:13:256 state
+    python tools/bench_xxz.py L [variants...]     variant = state | block[:m], e.g. block:12
 Times 20 applies with the context's CUDA-event profiler; GB/s counts 2 n s bytes (x read once, y written once)."""
 import importlib, os, sys
 import numpy as np
@@ -8,20 +8,18 @@ import __graft_entry__ as e
 pkg = e.load_package(); wl = importlib.import_module("lambda_lanczos_b200.workloads")
 ctx = pkg.Context(0)
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 28
-variants = sys.argv[2:] or ["state", "block:13:256", "block:13:512", "block:12:256", "block:14:256", "block:14:512", "block:11:256"]
+variants = sys.argv[2:] or ["state", "block", "block:11", "block:13"]
 dtypes = [np.float64, np.complex128] if L <= 28 else [np.float64]
 for dtype in dtypes:
     ref = None
     for v in variants:
         parts = v.split(":")
-        for k in ("LLZ_XXZ_KERNEL", "LLZ_XXZ_M", "LLZ_XXZ_THREADS"):
+        for k in ("LLZ_XXZ_KERNEL", "LLZ_XXZ_M"):
             os.environ.pop(k, None)
         if parts[0] == "state":
             os.environ["LLZ_XXZ_KERNEL"] = "state"
         if len(parts) > 1:
             os.environ["LLZ_XXZ_M"] = parts[1]
-        if len(parts) > 2:
-            os.environ["LLZ_XXZ_THREADS"] = parts[2]
         op = pkg.Operator.xxz(ctx, L, dtype=dtype)
         n = op.n
         x = pkg.Vector.from_host(ctx, wl.start_vector(n, dtype)); y = pkg.Vector(ctx, dtype, n)
