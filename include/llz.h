@@ -73,6 +73,10 @@ int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* ctx);
 int llz_ctx_destroy(llz_ctx_t ctx);
 int llz_ctx_synchronize(llz_ctx_t ctx);
 int llz_ctx_stream(llz_ctx_t ctx, void** cuda_stream);
+/* Copy between host and device memory in the context's stream order and wait for it (to_device != 0: host -> device).
+ * What a HOST-side mv_mul adapter needs (lambda_lanczos.hpp:120-126: the reference's mv_mul reads and writes host
+ * std::vectors): DeviceOperator<T>::host_function stages x out and y back in around the user's callable. */
+int llz_ctx_memcpy(llz_ctx_t ctx, void* dst, const void* src, size_t bytes, int to_device);
 /* A context keeps the device memory of destroyed vectors and of the last destroyed Krylov workspace (the mapped basis
  * slab) for reuse by the next run — mapping tens of GB of HBM costs as much as hundreds of Lanczos iterations.
  * This call returns all of it to the driver. */
@@ -160,6 +164,8 @@ int llz_vec_fill_zero(llz_vec_t v);
 int llz_vec_dot(llz_vec_t a, llz_vec_t b, double out[2]);
 /* *out = sqrt(Re<v,v>)                     (util::norm, linear_algebra.hpp:57-60) */
 int llz_vec_norm(llz_vec_t v, double* out);
+/* *out = sum_i |Re v_i| + |Im v_i|         (util::m_norm, linear_algebra.hpp:83-125: the _ASUM definition) */
+int llz_vec_m_norm(llz_vec_t v, double* out);
 /* v *= a                                   (util::scalar_mul, linear_algebra.hpp:66-72) */
 int llz_vec_scale(llz_vec_t v, const double a[2]);
 /* v *= 1/norm(v), *norm_out = norm before  (util::normalize, linear_algebra.hpp:78-80) */
@@ -223,7 +229,8 @@ typedef struct {
   int64_t max_iteration;          /* :138; <= 0 selects matrix_size */
   int64_t num_eigs_per_iteration; /* :173; <= 0 selects 5 */
   int orth;                       /* llz_orth_t; the reference behaviour is LLZ_ORTH_FULL */
-  int pipeline_depth;             /* iterations the GPU may run ahead of the host convergence test (0 = lock-step) */
+  int pipeline_depth;             /* iterations the GPU may run ahead of the host convergence test (0 = lock-step,
+                                     < 0 = chosen from the vector size: 4 below 4 MB, 2 below 32 MB, else 1) */
   int ritz_solver;                /* 0 = bisection on the nroot extreme Ritz values, 1 = full implicit QL every step */
 } llz_eigs_params_t;
 

@@ -262,6 +262,12 @@ class Vector:
         _check(lib().llz_vec_norm(self.h, C.byref(out)), "llz_vec_norm")
         return float(out.value)
 
+    def m_norm(self) -> float:
+        """util::m_norm: sum |Re v_i| + |Im v_i| (util/linear_algebra.hpp:83-125)."""
+        out = C.c_double(0)
+        _check(lib().llz_vec_m_norm(self.h, C.byref(out)), "llz_vec_m_norm")
+        return float(out.value)
+
     def scale(self, a):
         z = complex(a)
         _check(lib().llz_vec_scale(self.h, (C.c_double * 2)(z.real, z.imag)), "llz_vec_scale")
@@ -372,7 +378,7 @@ class LambdaLanczos:
         # host array handed out at the start of every Lanczos run (row-sharded: the LOCAL block); None = seeded default
         self.init_vector = None
         self.orthogonalization = ORTH_FULL
-        self.pipeline_depth = 1
+        self.pipeline_depth = -1  # auto: deeper for small vectors (launch-latency bound), see auto_pipeline_depth
         self.ritz_solver = 0
         self.want_eigenvectors = True
         self._iter_counts = []

@@ -185,6 +185,14 @@ int llz_ctx_synchronize(llz_ctx_t ctx) {
   return LLZ_OK;
 }
 
+int llz_ctx_memcpy(llz_ctx_t ctx, void* dst, const void* src, size_t bytes, int to_device) {
+  if (!ctx || (bytes > 0 && (!dst || !src))) return fail(LLZ_ERR_INVALID, "ctx_memcpy: null");
+  LLZ_CUDA(cudaSetDevice(ctx->device));
+  LLZ_CUDA(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LLZ_OK;
+}
+
 int llz_ctx_stream(llz_ctx_t ctx, void** s) {
   if (!ctx || !s) return fail(LLZ_ERR_INVALID, "null argument");
   *s = (void*)ctx->stream;
@@ -331,6 +339,19 @@ int llz_vec_norm(llz_vec_t v, double* out) {
   double d[2] = {0.0, 0.0};
   LLZ_TRY(dot_to_host(v->ctx, v->dtype, v->d, v->d, v->n, d));
   *out = sqrt(d[0]);
+  return LLZ_OK;
+}
+
+int llz_vec_m_norm(llz_vec_t v, double* out) {
+  if (!v || !out) return fail(LLZ_ERR_INVALID, "null");
+  llz_ctx_t ctx = v->ctx;
+  int grid = 0;
+  LLZ_TRY(launch_asum(ctx, v->dtype, v->d, v->n, ctx->d_partials, &grid));
+  LLZ_TRY(launch_sum_partials(ctx, ctx->d_partials, grid, 1, ctx->d_result, nullptr));
+  LLZ_TRY(comm_allreduce_sum(ctx, ctx->d_result, 1));
+  LLZ_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = ctx->h_result[0];
   return LLZ_OK;
 }
 

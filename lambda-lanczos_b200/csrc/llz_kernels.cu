@@ -691,6 +691,25 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const 
   finish_scalar(t, partials, msg, scratch);
 }
 
+// per-CTA partials of sum_i |Re v_i| + |Im v_i|  (util::m_norm, util/linear_algebra.hpp:83-125: the _ASUM definition)
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_asum(const T* __restrict__ x, int64_t n, double* partials) {
+  constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
+  __shared__ double scratch[kWarps];
+  double s = 0.0;
+  const int64_t npacks = (n + VEC - 1) / VEC;
+  for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < npacks; p += (int64_t)gridDim.x * kThreads) {
+    const int64_t idx = p * VEC;
+    Pack<T> a = (idx + VEC <= n) ? ld_plain(x + idx) : ld_guard(x, idx, n);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      s += fabs((double)comp(a.e[e], 0));
+      if (NC == 2) s += fabs((double)comp(a.e[e], 1));
+    }
+  }
+  const double t = block_sum(s, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
 // result[c] = sum_i partials[i*nc + c]; also mirrored to pinned host memory when h_result != null
 __global__ void __launch_bounds__(kThreads) k_sum_partials(const double* partials, int count, int nc, double* result, double* h_result) {
   __shared__ double scratch[kWarps];
@@ -977,6 +996,16 @@ int launch_dot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n
     *grid_out = grid;
   });
   return check_launch(ctx, "k_dot");
+}
+
+int launch_asum(llz_ctx_t ctx, int dtype, const void* a, int64_t n, double* partials, int* grid_out) {
+  LLZ_DISPATCH(dtype, {
+    const int64_t npacks = (n + Num<T>::VEC - 1) / Num<T>::VEC;
+    const int grid = persistent_grid(ctx, (npacks + kThreads - 1) / kThreads, 4);
+    k_asum<T><<<grid, kThreads, 0, ctx->stream>>>((const T*)a, n, partials);
+    *grid_out = grid;
+  });
+  return check_launch(ctx, "k_asum");
 }
 
 int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out,

@@ -110,6 +110,8 @@ int launch_combine(llz_ctx_t ctx, int dtype, const void* V, int64_t ld, int col0
                    int accumulate, double* norm_partials, int* grid_out);
 // partials of <a,b> (NC doubles per CTA, interleaved) and of Re<a,b> only
 int launch_dot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out);
+// partials of sum |Re a_i| + |Im a_i| (util::m_norm), one double per CTA
+int launch_asum(llz_ctx_t ctx, int dtype, const void* a, int64_t n, double* partials, int* grid_out);
 // partials of Re<a,b> only, one double per CTA (alpha when the operator cannot fuse the dot)
 int launch_redot(llz_ctx_t ctx, int dtype, const void* a, const void* b, int64_t n, double* partials, int* grid_out,
                  const PeerMsg& msg = PeerMsg());

@@ -6,6 +6,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "llz.h"
@@ -108,12 +109,26 @@ class Context {
   std::shared_ptr<llz_ctx_s> h_;
 };
 
-// Device vector of n_local elements of T.
+// Iterations the GPU runs ahead of the host's convergence test when the engine's `pipeline_depth` is negative (the
+// default): a Lanczos iteration at depth k streams (2k + 7) vectors, so with vectors of a few MB it is shorter than the
+// host's Ritz solve plus the launch latency and the launches must be queued several iterations ahead to keep the GPU
+// busy; with vectors of hundreds of MB one iteration ahead hides the host entirely, and every speculative iteration
+// past convergence is milliseconds thrown away — for the Exponentiator, which stops after ~10 iterations, one in ten,
+// so it runs in lock-step there.  `vector_bytes` must be the same on every rank of a row-sharded group (the ranks
+// replicate the control flow): pass global_rows * sizeof(T) / nranks.
+inline int auto_pipeline_depth(size_t vector_bytes, bool lanczos) {
+  if (vector_bytes < ((size_t)4 << 20)) return 4;
+  if (vector_bytes < ((size_t)32 << 20)) return 2;
+  return lanczos ? 1 : 0;
+}
+
+// Device vector of n_local elements of T.  Holds a reference to its context: the vector's memory goes back to the
+// context's pool when it dies, so the context must outlive it (e.g. eigenvectors returned by run_device()).
 template <typename T>
 class DeviceVector {
  public:
   DeviceVector() {}
-  DeviceVector(const Context& ctx, size_t n) : n_(n) {
+  DeviceVector(const Context& ctx, size_t n) : n_(n), ctx_(ctx) {
     llz_vec_t v = nullptr;
     check(llz_vec_create(ctx.get(), util::dtype_of<T>::value, (int64_t)n, &v), "llz_vec_create");
     h_.reset(v, [](llz_vec_t p) { llz_vec_destroy(p); });
@@ -136,8 +151,40 @@ class DeviceVector {
   }
 
  private:
-  std::shared_ptr<llz_vec_s> h_;
   size_t n_ = 0;
+  Context ctx_ = Context::none();  // declared before h_: destroyed after it
+  std::shared_ptr<llz_vec_s> h_;
 };
+
+// The reference's vector helpers (util/linear_algebra.hpp:30-144) on device vectors, same names and semantics.
+namespace util {
+template <typename T> inline T inner_prod(const DeviceVector<T>& v1, const DeviceVector<T>& v2) {  // conjugates v1 (:30-51)
+  double out[2] = {0, 0};
+  check(llz_vec_dot(v1.get(), v2.get(), out), "llz_vec_dot");
+  std::complex<double> z(out[0], out[1]);
+  return static_cast<T>(*reinterpret_cast<const typename std::conditional<std::is_same<T, real_t<T>>::value, double, std::complex<double>>::type*>(&z));
+}
+template <typename T> inline real_t<T> norm(const DeviceVector<T>& v) {  // :57-60
+  double out = 0;
+  check(llz_vec_norm(v.get(), &out), "llz_vec_norm");
+  return (real_t<T>)out;
+}
+template <typename T> inline real_t<T> m_norm(const DeviceVector<T>& v) {  // :83-125
+  double out = 0;
+  check(llz_vec_m_norm(v.get(), &out), "llz_vec_m_norm");
+  return (real_t<T>)out;
+}
+template <typename T> inline void scalar_mul(T a, DeviceVector<T>& v) {  // :66-72
+  double z[2];
+  to_pair(a, z);
+  check(llz_vec_scale(v.get(), z), "llz_vec_scale");
+}
+template <typename T> inline void normalize(DeviceVector<T>& v) { check(llz_vec_normalize(v.get(), nullptr), "llz_vec_normalize"); }  // :78-80
+template <typename T> inline void schmidt_orth(DeviceVector<T>& uorth, const std::vector<DeviceVector<T>>& us) {  // :133-144
+  std::vector<llz_vec_t> hs;
+  for (const auto& u : us) hs.push_back(u.get());
+  check(llz_vec_schmidt_orth(uorth.get(), hs.data(), (int64_t)hs.size(), 1), "llz_vec_schmidt_orth");
+}
+}  // namespace util
 
 }  // namespace lambda_lanczos_b200

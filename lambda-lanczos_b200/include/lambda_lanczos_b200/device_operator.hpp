@@ -3,6 +3,7 @@
 // (lambda_lanczos.hpp:126, exponentiator.hpp:41) becomes when the vectors live in HBM.  Copyable and reassignable
 // like the std::function it replaces; the underlying llz_op_t is shared.
 #pragma once
+#include <algorithm>
 #include <functional>
 #include <utility>
 
@@ -67,6 +68,26 @@ class DeviceOperator {
     DeviceOperator d(ctx, op, n);
     d.fn_ = holder;
     return d;
+  }
+
+  // The reference's own operator type (lambda_lanczos.hpp:120-126, exponentiator.hpp:35-41): a HOST callable that
+  // ADDS A*in to a zero-filled `out`.  The Krylov loop still runs on the GPU; every application copies the input vector
+  // to the host, calls `fn`, and copies the result back — the price of an operator that only exists as CPU code.  This is
+  // what lets source written against the reference (its samples, its tests) compile unchanged.
+  using HostFn = std::function<void(const std::vector<T>& in, std::vector<T>& out)>;
+  static DeviceOperator host_function(const Context& ctx, size_t n, HostFn fn) {
+    auto in = std::make_shared<std::vector<T>>(n);
+    auto out = std::make_shared<std::vector<T>>(n);
+    llz_ctx_t c = ctx.get();
+    return callback(
+        ctx, n,
+        [c, in, out, fn](const T* x_dev, T* y_dev, size_t len, void*) {
+          check(llz_ctx_memcpy(c, in->data(), x_dev, len * sizeof(T), 0), "llz_ctx_memcpy");
+          std::fill(out->begin(), out->end(), T());  // the reference hands mv_mul a zero-filled output (:242-243)
+          fn(*in, *out);
+          check(llz_ctx_memcpy(c, y_dev, out->data(), len * sizeof(T), 1), "llz_ctx_memcpy");
+        },
+        true);
   }
 
   // Non-owning view of an operator created through the C ABI.

@@ -31,11 +31,14 @@ class Exponentiator {
   bool full_orthogonalize = false;
   size_t initial_vector_size = 200;
 
-  // ---- engine knob: iterations the GPU may run ahead of the host overlap test ----
-  int pipeline_depth = 1;
+  // ---- engine knob: iterations the GPU may run ahead of the host overlap test (< 0: auto_pipeline_depth) ----
+  int pipeline_depth = -1;
 
   Exponentiator(DeviceOperator<T> mv_mul, size_t matrix_size)
       : mv_mul(std::move(mv_mul)), matrix_size(matrix_size), max_iteration(matrix_size) {}
+  // The reference's constructor, verbatim (exponentiator.hpp:80-82): a HOST mv_mul, see LambdaLanczos.
+  Exponentiator(std::function<void(const std::vector<T>&, std::vector<T>&)> host_mv_mul, size_t matrix_size)
+      : Exponentiator(DeviceOperator<T>::host_function(Context::default_context(), matrix_size, std::move(host_mv_mul)), matrix_size) {}
 
   // exponentiator.hpp:87-173 with device-resident input/output (no PCIe traffic per call: what a time-evolution loop
   // that feeds output back as input wants).  `output` may alias `input`.
@@ -60,7 +63,7 @@ class Exponentiator {
     const double beta_threshold = (double)std::numeric_limits<R>::epsilon();  // :154
     size_t itern = max_iteration;
     size_t enqueued = 0;
-    const size_t depth = pipeline_depth < 0 ? 0 : (size_t)pipeline_depth;
+    const size_t depth = pipeline_depth < 0 ? (size_t)auto_pipeline_depth(matrix_size * sizeof(T) / (size_t)ctx.nranks(), false) : (size_t)pipeline_depth;
     for (size_t k = 1; k <= max_iteration; ++k) {
       const size_t ahead = std::min(max_iteration, k + depth);
       while (enqueued < ahead) {

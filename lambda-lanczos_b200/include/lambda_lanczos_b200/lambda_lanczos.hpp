@@ -56,7 +56,7 @@ struct VectorRandomInitializer<std::complex<R>> {
 class KrylovWorkspace {
  public:
   KrylovWorkspace() {}
-  KrylovWorkspace(const Context& ctx, int dtype, size_t n, size_t max_cols) : n_(n), max_cols_(max_cols), dtype_(dtype) {
+  KrylovWorkspace(const Context& ctx, int dtype, size_t n, size_t max_cols) : ctx_(ctx), n_(n), max_cols_(max_cols), dtype_(dtype) {
     llz_krylov_t k = nullptr;
     check(llz_krylov_create(ctx.get(), dtype, (int64_t)n, (int64_t)max_cols, &k), "llz_krylov_create");
     h_.reset(k, [](llz_krylov_t p) { llz_krylov_destroy(p); });
@@ -70,6 +70,7 @@ class KrylovWorkspace {
   }
 
  private:
+  Context ctx_ = Context::none();  // the workspace's memory is owned by the context: keep it alive (declared first: dies last)
   std::shared_ptr<llz_krylov_s> h_;
   size_t n_ = 0, max_cols_ = 0;
   int dtype_ = -1;
@@ -145,7 +146,7 @@ class LambdaLanczos {
 
   // ---- engine knobs without a reference counterpart ----
   int orthogonalization = LLZ_ORTH_FULL;  // llz_orth_t
-  int pipeline_depth = 1;                 // iterations the GPU may run ahead of the host convergence test
+  int pipeline_depth = -1;                // iterations the GPU may run ahead of the host convergence test (< 0: auto_pipeline_depth)
   int ritz_solver = 0;                    // 0: bisection on the extreme values, 1: full implicit QL every iteration
   double reorth_eta = 0.5;                // repeat the Gram-Schmidt pass when beta < reorth_eta * ||w'|| (DGKS)
   // Row-sharded runs (the context joined a group): `matrix_size` stays the GLOBAL dimension and `init_vector` is asked
@@ -158,6 +159,11 @@ class LambdaLanczos {
 
   LambdaLanczos(DeviceOperator<T> mv_mul, size_t matrix_size, bool find_maximum, size_t num_eigs)
       : mv_mul(std::move(mv_mul)), matrix_size(matrix_size), max_iteration(matrix_size), find_maximum(find_maximum), num_eigs(num_eigs) {}
+  // The reference's constructor, verbatim (lambda_lanczos.hpp:200-206): mv_mul is a HOST callable (out += A*in on
+  // std::vectors).  It is wrapped in DeviceOperator<T>::host_function on the process-wide default context.
+  LambdaLanczos(std::function<void(const std::vector<T>&, std::vector<T>&)> host_mv_mul, size_t matrix_size, bool find_maximum, size_t num_eigs)
+      : LambdaLanczos(DeviceOperator<T>::host_function(Context::default_context(), matrix_size, std::move(host_mv_mul)), matrix_size,
+                      find_maximum, num_eigs) {}
 
   // One complete Lanczos run (lambda_lanczos.hpp:217-322) with device-resident inputs and outputs.
   size_t run_iteration(std::vector<real_t<T>>& eigvalues, std::vector<DeviceVector<T>>& eigvecs, size_t nroot,
@@ -198,7 +204,7 @@ class LambdaLanczos {
     const double zero_threshold = (double)std::numeric_limits<R>::epsilon() * 1e1;  // :279
     size_t itern = max_iteration;
     size_t enqueued = 0;
-    const size_t depth = pipeline_depth < 0 ? 0 : (size_t)pipeline_depth;
+    const size_t depth = pipeline_depth < 0 ? (size_t)auto_pipeline_depth(matrix_size * sizeof(T) / (size_t)ctx.nranks(), true) : (size_t)pipeline_depth;
 
     for (size_t k = 1; k <= max_iteration; ++k) {
       // keep the GPU up to `depth` iterations ahead; speculation stops at the store's capacity

@@ -438,6 +438,180 @@ void EXPONENTIATE_LARGE_MATRIX_AND_ZERO_DELTA() {  // :106-222 — periodic hopp
   EXPECT_EQ(exponentiator.taylor_run(cd(0, 0), input, output), (size_t)1);
 }
 
+// ---- the cases below use the reference's constructor VERBATIM: mv_mul is a host lambda over std::vectors
+//      (DeviceOperator<T>::host_function stages the vectors around it; the Krylov loop stays on the GPU) ----
+void SIMPLE_MATRIX_USE_COMPLEX_TYPE(bool fix_seed) {  // test/lambda_lanczos_test.cpp:310-341 and :343-373
+  using cd = complex<double>;
+  const size_t n = 3;
+  cd matrix[n][n] = {{2.0, 1.0, 1.0}, {1.0, 2.0, 1.0}, {1.0, 1.0, 2.0}};
+  auto matmul = [&](const vector<cd>& in, vector<cd>& out) {
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < n; ++j) out[i] += matrix[i][j] * in[j];
+  };
+  LambdaLanczos<cd> engine(matmul, n, true, 1);
+  if (fix_seed) engine.init_vector = vector_initializer<cd>;
+  double eigvalue;
+  vector<cd> eigvec(n);
+  engine.run(eigvalue, eigvec);
+  const cd phase = std::exp(cd(0.0, 1.0) * std::arg(eigvec[0]));
+  EXPECT_NEAR(4.0, eigvalue, std::abs(4.0 * engine.eps));
+  for (size_t i = 0; i < n; ++i) {
+    EXPECT_NEAR((phase / std::sqrt((double)n)).real(), eigvec[i].real(), std::abs(4.0 * engine.eps * 10));
+    EXPECT_NEAR((phase / std::sqrt((double)n)).imag(), eigvec[i].imag(), std::abs(4.0 * engine.eps * 10));
+  }
+}
+void SIMPLE_MATRIX_USE_COMPLEX_TYPE_FIXED() { SIMPLE_MATRIX_USE_COMPLEX_TYPE(true); }
+void SIMPLE_MATRIX_USE_COMPLEX_TYPE_NOT_FIX_RANDOM_SEED() { SIMPLE_MATRIX_USE_COMPLEX_TYPE(false); }
+
+// A matrix with an exactly known largest eigenpair: a random diagonal rotated by `rounds` random plane rotations
+// (Jacobi rotations for the symmetric case, 2x2 unitaries for the Hermitian one), the eigenvector rotated along.  The
+// random draws are made in the order of the reference's generators (:538-594, :639-712) so that std::mt19937(1) yields
+// the reference's very matrices.
+template <typename T, typename U2>
+void rotate_planes(vector<vector<T>>& a, vector<T>& v, size_t k, size_t l, const U2& u) {  // a <- U a U^H, v <- U v
+  const size_t n = a.size();
+  const T akk = a[k][k], akl = a[k][l], alk = a[l][k], all = a[l][l];
+  for (size_t i = 0; i < n; ++i) {
+    const T rk = u.kk * a[k][i] + u.kl * a[l][i], rl = u.lk * a[k][i] + u.ll * a[l][i];
+    a[k][i] = rk;
+    a[l][i] = rl;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    a[i][k] = ll::util::typed_conj(a[k][i]);
+    a[i][l] = ll::util::typed_conj(a[l][i]);
+  }
+  const T ckk = ll::util::typed_conj(u.kk), ckl = ll::util::typed_conj(u.kl), clk = ll::util::typed_conj(u.lk), cll = ll::util::typed_conj(u.ll);
+  a[k][k] = u.kk * (akk * ckk + akl * ckl) + u.kl * (alk * ckk + all * ckl);
+  a[k][l] = u.kk * (akk * clk + akl * cll) + u.kl * (alk * clk + all * cll);
+  a[l][k] = ll::util::typed_conj(a[k][l]);
+  a[l][l] = u.lk * (akk * clk + akl * cll) + u.ll * (alk * clk + all * cll);
+  const T vk = u.kk * v[k] + u.kl * v[l];
+  v[l] = u.lk * v[k] + u.ll * v[l];
+  v[k] = vk;
+}
+template <typename T> struct Plane { T kk, kl, lk, ll; };
+
+template <typename T, bool HERMITIAN>
+void known_extreme_matrix(vector<vector<T>>& a, vector<T>& eigvec, double& eigvalue, size_t n, size_t rounds) {
+  std::mt19937 eng(1);
+  std::uniform_int_distribution<size_t> dist_index(0, n - 1);
+  std::uniform_real_distribution<double> dist_angle(0.0, 2 * M_PI);
+  std::uniform_real_distribution<double> dist_element(1.0, n * 10);
+  a.assign(n, vector<T>(n, T()));
+  eigvec.assign(n, T());
+  eigvalue = 1.0;
+  size_t at = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double d = dist_element(eng);
+    a[i][i] = d;
+    if (d > eigvalue) {
+      eigvalue = d;
+      at = i;
+    }
+  }
+  eigvec[at] = 1.0;
+  for (size_t r = 0; r < rounds; ++r) {
+    const size_t k = dist_index(eng);
+    size_t l = dist_index(eng);
+    while (k == l) l = dist_index(eng);
+    const double theta = dist_angle(eng);
+    Plane<T> u;
+    if constexpr (HERMITIAN) {
+      const double phi1 = dist_angle(eng), phi2 = dist_angle(eng);
+      const T I_(0, 1);
+      u.kk = std::exp(I_ * phi1) * std::cos(theta);
+      u.kl = -std::exp(I_ * phi2) * std::sin(theta);
+      u.lk = std::exp(-I_ * phi2) * std::sin(theta);
+      u.ll = std::exp(-I_ * phi1) * std::cos(theta);
+    } else {
+      u.kk = std::cos(theta);
+      u.kl = -std::sin(theta);
+      u.lk = std::sin(theta);
+      u.ll = std::cos(theta);
+    }
+    rotate_planes(a, eigvec, k, l, u);
+  }
+}
+
+void RANDOM_SYMMETRIC_MATRIX() {  // test/lambda_lanczos_test.cpp:596-637
+  const size_t n = 50;
+  vector<vector<double>> matrix;
+  vector<double> correct_eigvec;
+  double correct_eigvalue = 0.0;
+  known_extreme_matrix<double, false>(matrix, correct_eigvec, correct_eigvalue, n, n * 10);
+  auto matmul = [&](const vector<double>& in, vector<double>& out) {
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < n; ++j) out[i] += matrix[i][j] * in[j];
+  };
+  LambdaLanczos<double> engine(matmul, n, true, 1);
+  engine.init_vector = vector_initializer<double>;
+  double eigvalue;
+  vector<double> eigvec(n);
+  engine.run(eigvalue, eigvec);
+  EXPECT_NEAR(correct_eigvalue, eigvalue, std::abs(correct_eigvalue * engine.eps));
+  const int sign = (eigvec[0] * correct_eigvec[0] > 0) ? 1 : -1;
+  for (size_t i = 0; i < n; ++i) EXPECT_NEAR(correct_eigvec[i] * sign, eigvec[i], std::abs(correct_eigvalue * engine.eps * n * n));
+}
+
+void RANDOM_HERMITIAN_MATRIX() {  // :714-755
+  using cd = complex<double>;
+  const size_t n = 10;
+  vector<vector<cd>> matrix;
+  vector<cd> correct_eigvec;
+  double correct_eigvalue = 0.0;
+  known_extreme_matrix<cd, true>(matrix, correct_eigvec, correct_eigvalue, n, n * 10);
+  auto matmul = [&](const vector<cd>& in, vector<cd>& out) {
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < n; ++j) out[i] += matrix[i][j] * in[j];
+  };
+  LambdaLanczos<cd> engine(matmul, n, true, 1);
+  engine.init_vector = vector_initializer<cd>;
+  engine.eps = 1e-14;
+  double eigvalue;
+  vector<cd> eigvec(n);
+  engine.run(eigvalue, eigvec);
+  EXPECT_NEAR(correct_eigvalue, eigvalue, std::abs(correct_eigvalue * engine.eps));
+  const cd phase = std::exp(cd(0, 1) * (std::arg(eigvec[0]) - std::arg(correct_eigvec[0])));
+  for (size_t i = 0; i < n; ++i) {
+    EXPECT_NEAR((correct_eigvec[i] * phase).real(), eigvec[i].real(), std::abs(correct_eigvalue * engine.eps * 10));
+    EXPECT_NEAR((correct_eigvec[i] * phase).imag(), eigvec[i].imag(), std::abs(correct_eigvalue * engine.eps * 10));
+  }
+}
+
+void MANHATTAN_NORM() {  // :93-100, on a device vector
+  using cd = complex<double>;
+  ll::DeviceVector<cd> v(*g_ctx, 2);
+  v.upload(vector<cd>{cd(1.0, 3.0), cd(-1.0, -1.0)});
+  EXPECT_NEAR(1.0 + 3.0 + 1.0 + 1.0, ll::util::m_norm(v), 0.0);
+  ll::DeviceVector<double> w(*g_ctx, 1001);
+  vector<double> h(1001);
+  double expect = 0;
+  for (size_t i = 0; i < h.size(); ++i) {
+    h[i] = (i % 2 ? -1.0 : 1.0) * (double)i * 0.25;
+    expect += std::abs(h[i]);
+  }
+  w.upload(h);
+  EXPECT_NEAR(expect, ll::util::m_norm(w), 1e-9);
+}
+
+// The reference's sample1_simple.cpp as it stands (host lambda, default random start vector, eigenvalue_offset absent).
+void SAMPLE1_UNCHANGED() {
+  const int n = 3;
+  double matrix[n][n] = {{2.0, 1.0, 1.0}, {1.0, 2.0, 1.0}, {1.0, 1.0, 2.0}};
+  auto mv_mul = [&](const vector<double>& in, vector<double>& out) {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) out[i] += matrix[i][j] * in[j];
+  };
+  LambdaLanczos<double> engine(mv_mul, n, true, 1);
+  vector<double> eigenvalues;
+  vector<vector<double>> eigenvectors;
+  engine.run(eigenvalues, eigenvectors);
+  EXPECT_NEAR(4.0, eigenvalues[0], 4.0 * engine.eps);
+  Exponentiator<double> expo(mv_mul, n);
+  vector<double> input = {1, 0, 0}, output(n);
+  EXPECT_EQ(expo.run(3.0, input, output), (size_t)3);
+}
+
 int main() {
   try {
     ll::Context ctx(0);
@@ -455,6 +629,12 @@ int main() {
     RUN(DEGENERATE_TRACE);
     RUN(EXPONENTIATE_REAL);
     RUN(EXPONENTIATE_LARGE_MATRIX_AND_ZERO_DELTA);
+    RUN(SIMPLE_MATRIX_USE_COMPLEX_TYPE_FIXED);
+    RUN(SIMPLE_MATRIX_USE_COMPLEX_TYPE_NOT_FIX_RANDOM_SEED);
+    RUN(RANDOM_SYMMETRIC_MATRIX);
+    RUN(RANDOM_HERMITIAN_MATRIX);
+    RUN(MANHATTAN_NORM);
+    RUN(SAMPLE1_UNCHANGED);
   } catch (const std::exception& e) {
     std::printf("EXCEPTION: %s\n", e.what());
     return 2;

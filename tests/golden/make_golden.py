@@ -76,5 +76,26 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reference_runs.npz"), **out)
 
 
+
+def sample_outputs():
+    """stdout of the reference's own sample programs (src/samples/sample{1,2,3,5}*.cpp, built against the reference's
+    headers with g++ -O2) -> tests/golden/reference_sample_outputs.json.  tests/test_gpu_cpp_api.py builds the SAME,
+    unmodified sources against this engine's compat headers and compares eigenvalues and eigenvectors."""
+    import json
+    import subprocess
+    import tempfile
+
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for s in ("1_simple", "2_sparse", "3_dynamic", "5_multiroot"):
+            exe = os.path.join(tmp, "ref_sample" + s)
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-I/root/reference/include/lambda_lanczos",
+                                   f"/root/reference/src/samples/sample{s}.cpp", "-o", exe])
+            out["sample" + s] = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_sample_outputs.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
+    sample_outputs()
