@@ -48,7 +48,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 # (dram__bytes_read.sum + dram__bytes_write.sum per launch over the algorithmic bytes of that very launch):
 # profiles/r01b_ncu_full_summary.txt (k = 151, n = 16.7 M): project 20.68 / 20.67 GB, update 20.36 / 20.53 GB;
 # profiles/r02_ncu_traffic_by_k.txt holds the same ratio at other k and at the per-GPU shape of an 8-GPU run.
-NCU_TRAFFIC_RATIO = {"project": 1.000, "update": 0.992}
+NCU_TRAFFIC_RATIO = {"project": 1.000, "update": 0.992, "orth": 0.996}
 NCU_TRAFFIC_SOURCE = "profiles/r01b_ncu_full_summary.txt, profiles/r02_ncu_traffic_by_k.txt"
 
 METRIC = "lanczos_iterations_per_second"
@@ -518,7 +518,7 @@ def run_ours(args, rank, world):
     # device time of the K steps on the launching stream (host control included), max over the ranks
     dt = grp.max(ev0.elapsed_time(ev1) * 1e-3)
     launches = ctx.launch_count() - launches0
-    families = ("spmv", "halo", "exchange", "project", "reduce", "update", "scale", "combine", "dot", "recurrence")
+    families = ("spmv", "halo", "exchange", "orth", "project", "reduce", "update", "scale", "combine", "dot", "recurrence")
     prof = {name: ctx.profile_read(name) for name in families}
     ctx.profile(False)
     clocks = sampler.stop()
@@ -526,7 +526,7 @@ def run_ours(args, rank, world):
 
     # ---- roofline of the dominant kernel family (the two basis-streaming GEMV passes), this rank's launches ----
     peak, peak_src = load_measured_peak()
-    dom = max(("project", "update"), key=lambda k: prof[k][0])
+    dom = max(("orth", "project", "update"), key=lambda k: prof[k][0])
     ms, cnt, by = prof[dom]
     achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     s = 8

@@ -149,8 +149,8 @@ int llz_ctx_create_on_stream(int device, void* cuda_stream, llz_ctx_t* out) {
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
   ctx->vec_pool_limit = (size_t)prop.totalGlobalMem / 4;
   {
-    const char* env = getenv("LLZ_PDL");
-    ctx->pdl = env && env[0] == '1';  // opt-in: measured 6 % SLOWER on config 1 (9.9k vs 10.6k it/s), neutral elsewhere
+    const char* env = getenv("LLZ_FUSED_ORTH");
+    ctx->fuse_orth = !(env && env[0] == '0');
   }
   if (cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -438,6 +438,7 @@ int llz_ctx_destroy(llz_ctx_t ctx) {
   ctx_trim(ctx);
   comm_destroy(ctx);
   ctx_trim(ctx);  // the exchange buffers comm_destroy handed back to the pool
+  if (ctx->d_bar) cudaFree(ctx->d_bar);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);

@@ -8,17 +8,6 @@
 
 namespace llz {
 
-// Programmatic dependent launch (opt-in, LLZ_PDL=1): the kernels of the Lanczos iteration are then launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization (llz_launch.hpp: launch_chain), so the launch of kernel N+1 is
-// processed — and its CTAs take over SMs as they drain — while kernel N is still running; N+1 then blocks here until N
-// has completed and its writes are visible.  First statement of every such kernel; a no-op under a plain launch.
-// Validated (all GPU tests pass with it) but measured no gain: 9.9k vs 10.6k it/s on config 1, equal on config 4 —
-// the persistent grids leave no room for early-resident dependents, and cudaLaunchKernelEx costs more on the host.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
 constexpr int kThreads = 256;          // every streaming kernel uses 8 warps per CTA
 constexpr int kWarps = kThreads / 32;
 

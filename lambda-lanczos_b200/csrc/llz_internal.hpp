@@ -81,7 +81,11 @@ struct llz_ctx_s {
   size_t vec_pool_bytes = 0;
   size_t vec_pool_limit = 0;              // set at creation (a quarter of the device memory)
   llz_krylov_t cached_krylov = nullptr;   // last destroyed Krylov workspace, revived by a matching llz_krylov_create
-  bool pdl = false;  // programmatic dependent launch between the kernels of an iteration (LLZ_PDL=1 switches it on)
+  // grid-wide barrier of the fused orthogonalisation kernel: a device counter that only ever grows, and its value
+  // after the launches enqueued so far (every launch adds 3 x its grid)
+  unsigned long long* d_bar = nullptr;
+  unsigned long long bar_count = 0;
+  bool fuse_orth = true;  // LLZ_FUSED_ORTH=0 keeps the separate kernels (A/B measurements, tests)
   // profiling
   bool profile = false;
   std::map<std::string, llz::ProfEntry> prof;

@@ -14,6 +14,7 @@
 // walks contiguous row slabs with 128-bit loads, keeps the w slab in registers across all columns, and reduces in a
 // fixed order (no floating-point atomics), so results are reproducible bit for bit.
 #include <algorithm>
+#include <map>
 
 #include "llz_device.cuh"
 #include "llz_launch.hpp"
@@ -132,11 +133,9 @@ __device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base,
 }
 
 template <class T, int VPT>
-__global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
-  pdl_prologue();
+__device__ __forceinline__ void project_body(const ProjectArgs& a, double* smem_d) {
   using R = typename Num<T>::R;
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
-  extern __shared__ __align__(16) double smem_d[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int width = a.ncols * NC;
   double* hs = smem_d;                     // [kWarps][width]
@@ -180,6 +179,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
   if (tid == 0) out[width] = wn;
 }
 
+template <class T, int VPT>
+__global__ void __launch_bounds__(kThreads, 2) k_project(ProjectArgs a) {
+  extern __shared__ __align__(16) double smem_d[];
+  project_body<T, VPT>(a, smem_d);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 struct ReduceArgs {
   const double* ph;
@@ -198,14 +203,15 @@ struct ReduceArgs {
 // 32 values per CTA; the 8 warps each add every 8th per-CTA partial (coalesced 256-byte rows), then the 8 partial sums
 // are added in a fixed order.  Row-sharded: the result goes straight into every peer's inbox over NVLink and the last
 // CTA to finish announces the message — no collective call between the projection and the update.
-__global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
-  pdl_prologue();
+// (`block` of `nblocks`: the kernel's CTAs, or the first CTAs of the fused kernel's grid; the per-CTA partials may have
+//  been written by other CTAs of the SAME launch there, hence the L2 loads)
+__device__ __forceinline__ void reduce_body(const ReduceArgs& a, int block, int nblocks) {
   __shared__ double part[kWarps][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + tx;
+  const int i = block * 32 + tx;
   double s = 0.0;
   if (i <= a.width)
-    for (int c = ty; c < a.grid; c += kWarps) s += a.ph[(size_t)c * (a.width + 1) + i];
+    for (int c = ty; c < a.grid; c += kWarps) s += __ldcg(a.ph + (size_t)c * (a.width + 1) + i);
   part[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && i <= a.width) {
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
     if (threadIdx.x == 0) {
       __threadfence_system();
       const unsigned int t = atomicAdd(a.ticket, 1u);
-      is_last = (t == gridDim.x - 1);
+      is_last = (t == (unsigned int)nblocks - 1);
       if (is_last) *a.ticket = 0;
     }
     __syncthreads();
@@ -241,6 +247,8 @@ __global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) {
     }
   }
 }
+
+__global__ void __launch_bounds__(kThreads) k_reduce(ReduceArgs a) { reduce_body(a, blockIdx.x, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------------------------------
 struct UpdateArgs {
@@ -362,10 +370,8 @@ __device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base,
 }
 
 template <class T, int VPT>
-__global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
-  pdl_prologue();
+__device__ __forceinline__ void update_body(const UpdateArgs& a, unsigned char* smem_u) {
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
-  extern __shared__ __align__(16) unsigned char smem_u[];
   T* cs = reinterpret_cast<T*>(smem_u);
   __shared__ double scratch[kWarps];
   const int tid = threadIdx.x;
@@ -377,8 +383,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
       const double im = NC == 2 ? peer_sum(a.coef_msg.ch, a.coef_msg.seq, col * NC + 1) : 0.0;
       return from_double<T>(re, im);
     }
-    const double* c = a.coef + (size_t)col * NC;
-    return from_double<T>(c[0], NC == 2 ? c[NC - 1] : 0.0);
+    const double* c = a.coef + (size_t)col * NC;  // (possibly written by other CTAs of this very launch: L2 loads)
+    return from_double<T>(__ldcg(c), NC == 2 ? __ldcg(c + NC - 1) : 0.0);
   };
   for (int i = tid; i < a.ncols; i += kThreads) cs[i] = coef_at(a.col0 + i);
   __syncthreads();
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
   R alpha = 0, beta = 0;
   T h1 = zero_of(T()), h2 = zero_of(T());
   if (a.fold >= 1) {
-    alpha = (R)(*a.alpha);
+    alpha = (R)__ldcg(a.alpha);
     h1 = coef_at(a.cu1);
     if (a.fold >= 2) {
       beta = (R)(*a.beta_prev);
@@ -407,6 +413,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
   }
 }
 
+template <class T, int VPT>
+__global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_u[];
+  update_body<T, VPT>(a, smem_u);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 struct ScaleNormArgs {
   void* x;
@@ -416,28 +428,27 @@ struct ScaleNormArgs {
   ScalarSink sink;
 };
 
-template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(ScaleNormArgs a) {
-  pdl_prologue();
-  using R = typename Num<T>::R;
-  constexpr int VEC = Num<T>::VEC;
-  __shared__ double scratch[kWarps];
-  const int tid = threadIdx.x;
+// beta = sqrt(||u||^2) from the per-CTA partials (or the peers' message), identically in every CTA; CTA 0 publishes the
+// iteration's scalars to the device bank and the pinned host mirror.  Call with all threads of the CTA.
+__device__ __forceinline__ double norm_and_publish(const ScaleNormArgs& a, double* scratch) {
   double beta2;
   if (a.sink.beta_msg.ch.G > 0) {
     peer_wait(a.sink.beta_msg.ch, a.sink.beta_msg.seq);
     beta2 = peer_sum(a.sink.beta_msg.ch, a.sink.beta_msg.seq, 0);
   } else {
-    beta2 = block_sum_partials(a.pb, a.npb, scratch);
+    double v = 0.0;
+    for (int i = threadIdx.x; i < a.npb; i += kThreads) v += __ldcg(a.pb + i);
+    beta2 = block_sum(v, scratch);
   }
   const double beta = sqrt(beta2);
-  if (blockIdx.x == 0 && tid == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (a.sink.beta_out) *a.sink.beta_out = beta;
     if (a.sink.h_beta) *a.sink.h_beta = beta;
-    if (a.sink.h_alpha && a.sink.alpha_in) *a.sink.h_alpha = *a.sink.alpha_in;
+    if (a.sink.h_alpha && a.sink.alpha_in) *a.sink.h_alpha = __ldcg(a.sink.alpha_in);
     if (a.sink.h_wnorm) {
       double wn = beta;
       if (a.sink.wnorm_msg.ch.G > 0) wn = sqrt(peer_sum(a.sink.wnorm_msg.ch, a.sink.wnorm_msg.seq, a.sink.wnorm_index));
-      else if (a.sink.wnorm2_in) wn = sqrt(*a.sink.wnorm2_in);
+      else if (a.sink.wnorm2_in) wn = sqrt(__ldcg(a.sink.wnorm2_in));
       *a.sink.h_wnorm = wn;
     }
     if (a.sink.h_flag) {
@@ -445,6 +456,15 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(S
       *reinterpret_cast<volatile long long*>(a.sink.h_flag) = a.sink.flag_value;
     }
   }
+  return beta;
+}
+
+template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(ScaleNormArgs a) {
+  using R = typename Num<T>::R;
+  constexpr int VEC = Num<T>::VEC;
+  __shared__ double scratch[kWarps];
+  const int tid = threadIdx.x;
+  const double beta = norm_and_publish(a, scratch);
   if (!(beta > 0.0) || !isfinite(beta)) return;  // breakdown: the reference leaves u_k un-normalised (:279-283)
   const R inv = (R)1 / (R)beta;                   // normalize() multiplies by T(1)/norm (linear_algebra.hpp:78-80)
   T* x = reinterpret_cast<T*>(a.x);
@@ -458,6 +478,79 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_scale_norm(S
   if (blockIdx.x == 0) {
     const int64_t i = npacks * VEC + tid;
     if (i < a.n) x[i] = scale_real(x[i], inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The whole orthogonalisation step of a Lanczos iteration in ONE launch: projection, reduction of the per-CTA partials,
+// update, norm and normalisation (k_project + k_reduce + k_update + k_scale_norm) separated by grid-wide barriers
+// instead of kernel boundaries.  Launched cooperatively (every CTA resident), one or two CTAs per SM as before; a
+// barrier costs one L2 atomic and a poll (~2 us) where a launch boundary costs the drain of the grid, the launch
+// latency and the host's launch work — at n = 100k that is half of the iteration, and row-sharded it is what the
+// three latency-bound launches per iteration were.  Same arithmetic, same order: bit-identical to the separate kernels.
+// ------------------------------------------------------------------------------------------------------------------
+struct OrthArgs {
+  ProjectArgs p;
+  ReduceArgs r;
+  int nred;  // CTAs that take part in the reduction (32 values each)
+  UpdateArgs u;
+  ScaleNormArgs s;
+  unsigned long long* bar;      // device counter, monotonic across launches
+  unsigned long long bar_base;  // its value when this launch starts
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Grid-wide barrier number `index` (1, 2, ...) of this launch.  Every CTA is resident (cooperative launch).
+__device__ __forceinline__ void grid_barrier(const OrthArgs& a, int index) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // this CTA's global writes (ordered before by the barrier above) are visible before it arrives
+    atomicAdd(a.bar, 1ull);
+    const unsigned long long target = a.bar_base + (unsigned long long)index * gridDim.x;
+    while (ld_acquire_gpu(a.bar) < target) {
+    }
+  }
+  __syncthreads();
+}
+
+template <class T, int VPT>
+__global__ void __launch_bounds__(kThreads, 2) k_orth(OrthArgs a) {
+  using R = typename Num<T>::R;
+  constexpr int VEC = Num<T>::VEC;
+  extern __shared__ __align__(16) unsigned char smem_o[];
+  __shared__ double scratch[kWarps];
+  project_body<T, VPT>(a.p, reinterpret_cast<double*>(smem_o));
+  grid_barrier(a, 1);
+  if ((int)blockIdx.x < a.nred) reduce_body(a.r, blockIdx.x, a.nred);
+  grid_barrier(a, 2);
+  update_body<T, VPT>(a.u, smem_o);  // (row-sharded: waits for the peers' coefficient messages in its prologue)
+  grid_barrier(a, 3);
+  const double beta = norm_and_publish(a.s, scratch);
+  if (!(beta > 0.0) || !isfinite(beta)) return;
+  const R inv = (R)1 / (R)beta;
+  // every thread re-scales exactly the packets it wrote in the update phase (same slab walk)
+  T* x = reinterpret_cast<T*>(a.u.out);
+  constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
+  const int64_t nslabs = (a.u.n + SLAB - 1) / SLAB;
+  for (int64_t sl = blockIdx.x; sl < nslabs; sl += gridDim.x) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int64_t idx = sl * SLAB + (int64_t)(i * kThreads + threadIdx.x) * VEC;
+      if (idx + VEC <= a.u.n) {
+        Pack<T> v = ld_plain(x + idx);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v.e[e] = scale_real(v.e[e], inv);
+        st_pack(x + idx, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if (idx + e < a.u.n) x[idx + e] = scale_real(x[idx + e], inv);
+      }
+    }
   }
 }
 
@@ -480,7 +573,6 @@ struct RecurrenceArgs {
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
-  pdl_prologue();
   using R = typename Num<T>::R;
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
@@ -674,7 +766,6 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_dot(const T*
 }
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_redot(const T* __restrict__ x, const T* __restrict__ y, int64_t n, double* partials, PeerMsg msg) {
-  pdl_prologue();
   constexpr int VEC = Num<T>::VEC;
   __shared__ double scratch[kWarps];
   double re = 0.0;
@@ -812,10 +903,9 @@ static int project_impl(llz_ctx_t ctx, const ProjectArgs& a, int* grid_out) {
   return check_launch(ctx, "k_project");
 }
 
-int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n,
-                   const Fold& fold, double* ph, int* grid_out) {
+static int make_project_args(int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n, const Fold& fold,
+                             double* ph, ProjectArgs& a) {
   if (ncols < 0 || ncols > max_project_cols(dtype)) return fail(LLZ_ERR_INVALID, "project: %d columns per launch", ncols);
-  ProjectArgs a;
   a.V = cs.V;
   a.ld = cs.ld;
   a.Q = cs.Q;
@@ -836,6 +926,13 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
   a.u2 = cs.nv >= 2 ? (const char*)cs.V + (size_t)(cs.nv - 2) * cs.ld * es : nullptr;
   if (a.fold >= 1 && !a.u1) return fail(LLZ_ERR_INVALID, "project: fold needs a previous basis column");
   if (a.fold >= 2 && !a.u2) return fail(LLZ_ERR_INVALID, "project: fold=2 needs two previous basis columns");
+  return LLZ_OK;
+}
+
+int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, int64_t n,
+                   const Fold& fold, double* ph, int* grid_out) {
+  ProjectArgs a;
+  LLZ_TRY(make_project_args(dtype, cs, col0, ncols, w, n, fold, ph, a));
   LLZ_DISPATCH(dtype, {
     if (pick_vpt<T>(ctx, n) == 2) return project_impl<T, 2>(ctx, a, grid_out);
     return project_impl<T, 1>(ctx, a, grid_out);
@@ -843,10 +940,9 @@ int launch_project(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int 
   return LLZ_OK;
 }
 
-int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2,
-                  const PeerMsg& msg, int wnorm_index, int publish) {
+static void make_reduce_args(int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2,
+                             const PeerMsg& msg, int wnorm_index, int publish, ReduceArgs& a) {
   const int nc = dtype_nc(dtype);
-  ReduceArgs a;
   a.ph = ph;
   a.grid = grid;
   a.wnorm2 = wnorm2;
@@ -857,6 +953,12 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
   a.wnorm_index = wnorm_index;
   a.publish = publish;
   a.ticket = msg.ticket;
+}
+
+int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0, int ncols, double* coef, double* wnorm2,
+                  const PeerMsg& msg, int wnorm_index, int publish) {
+  ReduceArgs a;
+  make_reduce_args(dtype, ph, grid, col0, ncols, coef, wnorm2, msg, wnorm_index, publish, a);
   cudaError_t le = launch_chain(ctx, k_reduce, (a.width + 1 + 31) / 32, kThreads, 0, a);
   if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_reduce: %s", cudaGetErrorString(le));
   return check_launch(ctx, "k_reduce");
@@ -874,11 +976,10 @@ static int update_impl(llz_ctx_t ctx, const UpdateArgs& a, int* grid_out) {
   return check_launch(ctx, "k_update");
 }
 
-int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
-                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
-                  const PeerMsg& coef_msg, const PeerMsg& norm_msg) {
+static int make_update_args(int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out, int64_t n,
+                            const double* coef, const Fold& fold, double* norm_partials, const PeerMsg& coef_msg,
+                            const PeerMsg& norm_msg, UpdateArgs& a) {
   if (ncols < 0 || ncols > max_update_cols(dtype)) return fail(LLZ_ERR_INVALID, "update: %d columns per launch", ncols);
-  UpdateArgs a;
   a.V = cs.V;
   a.ld = cs.ld;
   a.Q = cs.Q;
@@ -903,9 +1004,104 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
   a.cu2 = cs.nq + cs.nv - 2;
   if (a.fold >= 1 && (!a.u1 || !a.alpha)) return fail(LLZ_ERR_INVALID, "update: fold needs a previous basis column and alpha");
   if (a.fold >= 2 && (!a.u2 || !a.beta_prev)) return fail(LLZ_ERR_INVALID, "update: fold=2 needs two previous basis columns and beta");
+  return LLZ_OK;
+}
+
+int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
+                  int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
+                  const PeerMsg& coef_msg, const PeerMsg& norm_msg) {
+  UpdateArgs a;
+  LLZ_TRY(make_update_args(dtype, cs, col0, ncols, w, out, n, coef, fold, norm_partials, coef_msg, norm_msg, a));
   LLZ_DISPATCH(dtype, {
     if (pick_vpt<T>(ctx, n) == 2) return update_impl<T, 2>(ctx, a, grid_out);
     return update_impl<T, 1>(ctx, a, grid_out);
+  });
+  return LLZ_OK;
+}
+
+// The fused orthogonalisation step (k_orth): one cooperative launch for project + reduce + update + norm + normalise of
+// a full-reorthogonalisation iteration whose columns fit one projection chunk.  *fused = 0 (nothing launched) when the
+// shape does not allow it (too many columns for the shared-memory accumulators, or the grid would not be co-resident).
+// Resident CTAs per SM of k_orth for a given amount of dynamic shared memory (cached: the query costs microseconds).
+template <class T, int VPT> static int orth_ctas_per_sm(size_t smem) {
+  static std::map<size_t, int> cache;
+  auto it = cache.find(smem);
+  if (it != cache.end()) return it->second;
+  int per_sm = 0;
+  if (set_smem(k_orth<T, VPT>, smem) != LLZ_OK) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orth<T, VPT>, kThreads, smem) != cudaSuccess) per_sm = 0;
+  cache[smem] = per_sm;
+  return per_sm;
+}
+template <class T> static size_t orth_smem(int total_cols) {
+  // 4 KB granules: the shared-memory attribute and the occupancy query are then made once per granule, not per iteration
+  const size_t need = std::max(((size_t)kWarps * total_cols * Num<T>::NC + kWarps) * sizeof(double), std::max<size_t>(16, (size_t)total_cols * sizeof(T)));
+  return (need + 4095) / 4096 * 4096;
+}
+template <class T, int VPT> static int orth_grid(llz_ctx_t ctx, int total_cols, int64_t n) {
+  const int per_sm = orth_ctas_per_sm<T, VPT>(orth_smem<T>(total_cols));
+  if (per_sm < 1) return 0;
+  const int64_t nslabs = (n + slab_rows<T>(VPT) - 1) / slab_rows<T>(VPT);
+  const int grid = persistent_grid(ctx, nslabs, std::min(per_sm, 2));
+  return (total_cols * Num<T>::NC + 1 + 31) / 32 <= grid ? grid : 0;  // the reduction needs one CTA per 32 values
+}
+
+template <class T, int VPT>
+static int orth_impl(llz_ctx_t ctx, OrthArgs& a, int* fused, int* grid_out) {
+  const int grid = orth_grid<T, VPT>(ctx, a.p.ncols, a.p.n);
+  if (grid < 1) {
+    *fused = 0;
+    return LLZ_OK;
+  }
+  const size_t smem = orth_smem<T>(a.p.ncols);
+  a.nred = (a.r.width + 1 + 31) / 32;
+  if (!ctx->d_bar) {
+    LLZ_CUDA(cudaMalloc(&ctx->d_bar, sizeof(unsigned long long)));
+    LLZ_CUDA(cudaMemsetAsync(ctx->d_bar, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->bar_count = 0;
+  }
+  a.r.grid = grid;
+  a.s.npb = grid;
+  a.bar = ctx->d_bar;
+  a.bar_base = ctx->bar_count;
+  ctx->bar_count += 3ull * (unsigned long long)grid;
+  void* params[] = {&a};
+  cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_orth<T, VPT>, dim3((unsigned)grid), dim3(kThreads), params, smem, ctx->stream);
+  if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_orth: %s", cudaGetErrorString(le));
+  *fused = 1;
+  *grid_out = grid;
+  return check_launch(ctx, "k_orth");
+}
+
+bool orth_fusable(llz_ctx_t ctx, int dtype, int total_cols, int64_t n) {
+  if (total_cols < 1 || total_cols > max_project_cols(dtype)) return false;
+  switch (dtype) {
+    case LLZ_F32: return (pick_vpt<float>(ctx, n) == 2 ? orth_grid<float, 2>(ctx, total_cols, n) : orth_grid<float, 1>(ctx, total_cols, n)) > 0;
+    case LLZ_F64: return (pick_vpt<double>(ctx, n) == 2 ? orth_grid<double, 2>(ctx, total_cols, n) : orth_grid<double, 1>(ctx, total_cols, n)) > 0;
+    case LLZ_C64: return (pick_vpt<float2>(ctx, n) == 2 ? orth_grid<float2, 2>(ctx, total_cols, n) : orth_grid<float2, 1>(ctx, total_cols, n)) > 0;
+    case LLZ_C128: return (pick_vpt<double2>(ctx, n) == 2 ? orth_grid<double2, 2>(ctx, total_cols, n) : orth_grid<double2, 1>(ctx, total_cols, n)) > 0;
+  }
+  return false;
+}
+
+int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t n, const Fold& fold, double* ph, double* coef,
+                double* wnorm2, const PeerMsg& coef_msg, int wnorm_index, double* norm_partials, const ScalarSink& sink, int* fused,
+                int* grid_out) {
+  *fused = 0;
+  const int total = cs.ncols();
+  if (total < 1 || total > max_project_cols(dtype)) return LLZ_OK;
+  OrthArgs a;
+  LLZ_TRY(make_project_args(dtype, cs, 0, total, w, n, fold, ph, a.p));
+  make_reduce_args(dtype, ph, 0, 0, total, coef, wnorm2, coef_msg, wnorm_index, 1, a.r);
+  LLZ_TRY(make_update_args(dtype, cs, 0, total - fold.mode, w, w, n, coef, fold, norm_partials, coef_msg, fold.norm_msg, a.u));
+  a.s.x = w;
+  a.s.n = n;
+  a.s.pb = norm_partials;
+  a.s.npb = 0;
+  a.s.sink = sink;
+  LLZ_DISPATCH(dtype, {
+    if (pick_vpt<T>(ctx, n) == 2) return orth_impl<T, 2>(ctx, a, fused, grid_out);
+    return orth_impl<T, 1>(ctx, a, fused, grid_out);
   });
   return LLZ_OK;
 }

@@ -523,6 +523,36 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     cs.Q = (const void* const*)kry->d_qptrs;
     cs.nq = kry->nq;
     if (orth != LLZ_ORTH_FULL_TWICE) fold.norm_msg = sink.beta_msg;
+    // One cooperative launch for project + reduce + update + norm + normalise when the columns fit one projection
+    // chunk and the scalars travel through peer memory (or there is one rank); else the separate kernels below.
+    const int total = cs.ncols(), nc = dtype_nc(kry->dtype);
+    const bool peer = comm_p2p(ctx) && total * nc + 1 <= comm_coef_capacity(ctx);
+    if (orth == LLZ_ORTH_FULL && ctx->fuse_orth && (ctx->nranks == 1 || peer) && orth_fusable(ctx, kry->dtype, total, kry->n)) {
+      const int max_grid = std::min(kMaxGrid, ctx->num_sms * 2);
+      LLZ_TRY(ensure_ph(kry, (size_t)max_grid * ((size_t)total * nc + 1)));
+      PeerMsg coef_msg;
+      if (peer) {
+        coef_msg = comm_next_message(ctx, kChanCoef);
+        sink.wnorm_msg = coef_msg;
+        sink.wnorm_index = total * nc;
+      }
+      sink.beta_out = kry->d_beta + (k - 1);
+      sink.alpha_in = kry->d_alpha + (k - 1);
+      sink.h_alpha = kry->h_alpha + (k - 1);
+      sink.h_beta = kry->h_beta + (k - 1);
+      sink.h_wnorm = kry->h_wnorm + (k - 1);
+      sink.wnorm2_in = kry->d_misc + 1;
+      sink.h_flag = kry->h_flag;
+      sink.flag_value = k;
+      const double es = (double)dtype_size(kry->dtype);
+      ProfScope ps(ctx, "orth", (double)kry->n * es * ((total + 1 + fold.mode) + (total + 2) + 2));
+      int fused = 0;
+      LLZ_TRY(launch_orth(ctx, kry->dtype, cs, y, kry->n, fold, kry->d_ph, kry->d_coef, kry->d_misc + 1, coef_msg, peer ? total * nc : -1,
+                          kry->d_pb, sink, &fused, &grid));
+      if (!fused) return fail(LLZ_ERR_CUDA, "krylov_step: the fused orthogonalisation kernel declined a shape it had accepted");
+      kry->k = k;
+      return LLZ_OK;
+    }
     LLZ_TRY(cgs_pass(kry, cs, y, fold, orth != LLZ_ORTH_FULL_TWICE, &grid, &sink.wnorm_msg, &sink.wnorm_index));
     if (orth == LLZ_ORTH_FULL_TWICE) {
       Fold nofold;

@@ -8,25 +8,11 @@
 namespace llz {
 
 #ifdef __CUDACC__
-// Launch a kernel of the per-iteration chain: a plain launch, or with programmatic stream serialisation (see
-// pdl_prologue in llz_device.cuh) when the context has it switched on (LLZ_PDL=1).
+// Launch a kernel of the per-iteration chain on the context's stream.
 template <class... KArgs, class... Args>
 inline cudaError_t launch_chain(llz_ctx_t ctx, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
-  if (!ctx->pdl) {
-    kernel<<<grid, block, smem, ctx->stream>>>(KArgs(args)...);
-    return cudaGetLastError();
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3((unsigned)block, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  kernel<<<grid, block, smem, ctx->stream>>>(KArgs(args)...);
+  return cudaGetLastError();
 }
 #endif
 
@@ -97,6 +83,13 @@ int launch_reduce(llz_ctx_t ctx, int dtype, const double* ph, int grid, int col0
 int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int ncols, const void* w, void* out,
                   int64_t n, const double* coef, const Fold& fold, double* norm_partials, int* grid_out,
                   const PeerMsg& coef_msg = PeerMsg(), const PeerMsg& norm_msg = PeerMsg());
+// One cooperative launch for the whole orthogonalisation step of a full-reorthogonalisation iteration: project on all
+// columns of `cs` (recurrence folded per `fold`), reduce, update `w` in place, norm, normalise, publish per `sink`.
+// *fused = 0 and nothing is launched when the shape does not allow it; the caller then issues the separate kernels.
+bool orth_fusable(llz_ctx_t ctx, int dtype, int total_cols, int64_t n);  // ask BEFORE drawing peer messages for the step
+int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t n, const Fold& fold, double* ph, double* coef,
+                double* wnorm2, const PeerMsg& coef_msg, int wnorm_index, double* norm_partials, const ScalarSink& sink, int* fused,
+                int* grid_out);
 // x *= 1/sqrt(sum partials); publishes beta (and alpha) per `sink`.  Leaves x untouched when the norm is not > 0.
 int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
                          const ScalarSink& sink);

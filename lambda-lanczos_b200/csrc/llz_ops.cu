@@ -53,7 +53,6 @@ struct HaloPush {
 template <class T>
 __global__ void __launch_bounds__(kThreads) k_halo_push(const T* __restrict__ x, const int32_t* __restrict__ idx, long long n_send, HaloPush hp, PeerMsg msg) {
   __shared__ int last_cta;
-  pdl_prologue();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_send; i += (long long)gridDim.x * kThreads) {
     int q = 0;
     while (i >= hp.start[q + 1]) ++q;
@@ -79,7 +78,6 @@ __global__ void __launch_bounds__(kThreads, 4)
                    const T* __restrict__ x, const T* halo, int32_t nloc, T* __restrict__ y, int64_t n,
                    typename Num<T>::R sigma, double* pa, PeerMsg msg, PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
-  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);  // the peers' entries of x have landed in `halo`
   constexpr int ROWS = kThreads / LPR;
   const int tid = threadIdx.x;
@@ -120,7 +118,6 @@ __global__ void __launch_bounds__(kThreads, 4)
                      const T* __restrict__ x, const T* halo, int32_t nloc, T* __restrict__ y, int64_t n,
                      typename Num<T>::R sigma, double* pa, int R, int cap, PeerMsg msg, PeerMsg halo_msg) {
   extern __shared__ __align__(16) unsigned char smem_s[];
-  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   T* prod = reinterpret_cast<T*>(smem_s);
   IDX* rp = reinterpret_cast<IDX*>(prod + cap);
@@ -232,7 +229,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
                     T* __restrict__ y, int64_t n, int64_t n_slices, typename Num<T>::R sigma, double* pa, PeerMsg msg,
                     PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
-  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   constexpr int U = 2;  // slices per warp step
   const int lane = threadIdx.x & 31;
@@ -339,7 +335,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   __shared__ double scratch[kWarps];
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ long long sp[STAGES][kTmaChunk + 1];
-  pdl_prologue();
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t stage_bytes = (size_t)cap * (sizeof(T) + sizeof(int32_t));

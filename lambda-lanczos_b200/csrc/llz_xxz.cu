@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(kThreads, 6)
   __shared__ double scratch[kWarps];
   __shared__ uint32_t pascal[32 * 33];  // pascal[b*33 + c] = C(b, c); the odd stride spreads rows over the banks
   for (int i = threadIdx.x; i < 32 * 32; i += kThreads) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
-  pdl_prologue();  // (the table above depends on nothing an earlier kernel wrote, so it is built while that one drains)
   if (SHARDED && gather_msg.ch.G > 0) peer_wait(gather_msg.ch, gather_msg.seq);  // the peers' blocks have landed in x_all
   R inv = (R)1;
   const bool rescale = SHARDED && p.x_scale != nullptr;
@@ -255,7 +254,6 @@ __global__ void __launch_bounds__(NT, xxz_min_blocks<T, NT, R, D>())
   __shared__ XxzBlockDesc desc[3];  // block it % 3: written one block ahead, while the slowest warp may still read it - 1
   const int tid = threadIdx.x;
   for (int i = tid; i < 32 * 32; i += NT) pascal[(i >> 5) * 33 + (i & 31)] = (uint32_t)c_binom[i >> 5][i & 31];
-  pdl_prologue();
   // shared memory: two x tiles of bsmax + 1 elements (the last one is the zero the padding entries of the neighbour
   // lists point at) | neighbour offsets [bsmax][E] (E = m - 1 rounded up to 4: a row's list is E/4 8-byte loads) |
   // meta [bsmax] | low states [bsmax]
