@@ -109,6 +109,16 @@ class Context {
   std::shared_ptr<llz_ctx_s> h_;
 };
 
+namespace detail {
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield");
+#endif
+}
+}  // namespace detail
+
 // Iterations the GPU runs ahead of the host's convergence test when the engine's `pipeline_depth` is negative (the
 // default): a Lanczos iteration at depth k streams (2k + 7) vectors, so with vectors of a few MB it is shorter than the
 // host's Ritz solve plus the launch latency and the launches must be queued several iterations ahead to keep the GPU

@@ -13,7 +13,10 @@
 //     eigenvectors ("locked" vectors for deflation) never leave HBM between Lanczos runs.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <exception>
+#include <thread>
 #include <cmath>
 #include <functional>
 #include <limits>
@@ -148,6 +151,7 @@ class LambdaLanczos {
   int orthogonalization = LLZ_ORTH_FULL;  // llz_orth_t
   int pipeline_depth = -1;                // iterations the GPU may run ahead of the host convergence test (< 0: auto_pipeline_depth)
   int ritz_solver = 0;                    // 0: bisection on the extreme values, 1: full implicit QL every iteration
+  int host_threads = 0;                   // 1: never start the helper thread that runs the Ritz solves of short iterations
   double reorth_eta = 0.5;                // repeat the Gram-Schmidt pass when beta < reorth_eta * ||w'|| (DGKS)
   // Row-sharded runs (the context joined a group): `matrix_size` stays the GLOBAL dimension and `init_vector` is asked
   // for the whole start vector, of which this rank keeps rows [row_offset, row_offset + rows) — so a seeded
@@ -203,38 +207,13 @@ class LambdaLanczos {
     tridiagonal::ExtremeState<double> warm;
     const double zero_threshold = (double)std::numeric_limits<R>::epsilon() * 1e1;  // :279
     size_t itern = max_iteration;
-    size_t enqueued = 0;
     const size_t depth = pipeline_depth < 0 ? (size_t)auto_pipeline_depth(matrix_size * sizeof(T) / (size_t)ctx.nranks(), true) : (size_t)pipeline_depth;
 
-    for (size_t k = 1; k <= max_iteration; ++k) {
-      // keep the GPU up to `depth` iterations ahead; speculation stops at the store's capacity
-      const size_t ahead = std::min(max_iteration, k + depth);
-      while (enqueued < ahead) {
-        if (enqueued + 2 > capacity) {
-          if (enqueued >= k) break;  // only speculative work would not fit
-          throw Error(LLZ_ERR_OOM, "LambdaLanczos: the Krylov basis is full after " + std::to_string(enqueued) +
-                                       " iterations; lower max_iteration (the algorithm stores every Lanczos vector)");
-        }
-        check(llz_krylov_step(kry, mv_mul.get(), (double)eigenvalue_offset, orthogonalization), "llz_krylov_step");
-        ++enqueued;
-      }
-      double a = 0, b = 0, wn = 0;
-      check(llz_krylov_fetch(kry, (int64_t)k, &a, &b, &wn), "llz_krylov_fetch");
-      // DGKS test: if the Gram-Schmidt pass removed most of the vector (near breakdown, e.g. the Krylov space of a
-      // deflated run is exhausted), one classical pass leaves it non-orthogonal: repeat the pass ("twice is enough").
-      // The reference's modified Gram-Schmidt does not need this; it keeps the same vector to rounding.
-      for (int pass = 0; pass < 3 && orthogonalization != LLZ_ORTH_RECURRENCE && b >= zero_threshold && b < reorth_eta * wn; ++pass) {
-        double shrink = 1.0;
-        check(llz_krylov_refine(kry, (int64_t)k, &shrink), "llz_krylov_refine");
-        enqueued = k;
-        wn = b;
-        b *= shrink;
-        ++stats_.refinements;
-      }
+    // The host side of iteration k once its scalars are known: Ritz values of T_k, then the reference's stopping rules.
+    auto host_step = [&](size_t k, double a, double b) -> bool {
       const auto t0 = clock::now();
       alpha.push_back(a);  // :248
       beta.push_back(b);   // :262
-
       const size_t ncalc = std::min(nroot, alpha.size());  // :264
       if (ritz_solver == 1) {
         std::vector<double> all;
@@ -244,7 +223,6 @@ class LambdaLanczos {
       } else {
         tridiagonal::extreme_eigenvalues(alpha.data(), beta.data(), alpha.size(), ncalc, find_maximum, evs, &warm);
       }
-
       bool stop = false;
       if (beta.back() < zero_threshold) {  // :279-283 (the new vector is left un-normalised and never used)
         itern = k;
@@ -263,7 +241,114 @@ class LambdaLanczos {
         }
       }
       stats_.seconds_host += std::chrono::duration<double>(clock::now() - t0).count();
-      if (stop) break;
+      return stop;
+    };
+    // DGKS test: if the Gram-Schmidt pass removed most of the vector (near breakdown, e.g. the Krylov space of a
+    // deflated run is exhausted), one classical pass leaves it non-orthogonal: repeat the pass ("twice is enough").
+    // The reference's modified Gram-Schmidt does not need this; it keeps the same vector to rounding.
+    auto needs_refinement = [&](double b, double wn) {
+      return orthogonalization != LLZ_ORTH_RECURRENCE && b >= zero_threshold && b < reorth_eta * wn;
+    };
+    auto enqueue_step = [&]() { check(llz_krylov_step(kry, mv_mul.get(), (double)eigenvalue_offset, orthogonalization), "llz_krylov_step"); };
+    auto basis_full = [&](size_t enqueued) {
+      return Error(LLZ_ERR_OOM, "LambdaLanczos: the Krylov basis is full after " + std::to_string(enqueued) +
+                                    " iterations; lower max_iteration (the algorithm stores every Lanczos vector)");
+    };
+
+    if (depth < 2 || host_threads == 1) {
+      // ---- one host thread: enqueue up to `depth` iterations ahead, then wait for iteration k and test it ----
+      size_t enqueued = 0;
+      for (size_t k = 1; k <= max_iteration; ++k) {
+        const size_t ahead = std::min(max_iteration, k + depth);
+        while (enqueued < ahead) {
+          if (enqueued + 2 > capacity) {
+            if (enqueued >= k) break;  // only speculative work would not fit
+            throw basis_full(enqueued);
+          }
+          enqueue_step();
+          ++enqueued;
+        }
+        double a = 0, b = 0, wn = 0;
+        check(llz_krylov_fetch(kry, (int64_t)k, &a, &b, &wn), "llz_krylov_fetch");
+        for (int pass = 0; pass < 3 && needs_refinement(b, wn); ++pass) {
+          double shrink = 1.0;
+          check(llz_krylov_refine(kry, (int64_t)k, &shrink), "llz_krylov_refine");
+          enqueued = k;
+          wn = b;
+          b *= shrink;
+          ++stats_.refinements;
+        }
+        if (host_step(k, a, b)) break;
+      }
+    } else {
+      // ---- two host threads (short iterations: the Ritz solve of T_k costs as much as the GPU's iteration).  This
+      //      thread only launches, up to `depth` iterations ahead of the last TESTED one; a helper waits for each
+      //      iteration's scalars (it spins on the pinned flag the GPU writes), runs the Ritz solve and the stopping
+      //      rules, and asks this thread for the rare DGKS refinement, the only other call that touches the workspace.
+      std::atomic<size_t> enqueued{0}, tested{0}, refine_request{0};
+      std::atomic<bool> refine_done{false}, finished{false}, abort_helper{false};
+      double refine_shrink = 1.0;
+      std::exception_ptr helper_error;
+      std::thread helper([&]() {
+        try {
+          for (size_t k = 1; k <= max_iteration; ++k) {
+            while (enqueued.load(std::memory_order_acquire) < k) {
+              if (abort_helper.load(std::memory_order_acquire)) return;
+              detail::cpu_relax();
+            }
+            double a = 0, b = 0, wn = 0;
+            check(llz_krylov_fetch(kry, (int64_t)k, &a, &b, &wn), "llz_krylov_fetch");
+            for (int pass = 0; pass < 3 && needs_refinement(b, wn); ++pass) {
+              refine_done.store(false, std::memory_order_relaxed);
+              refine_request.store(k, std::memory_order_release);
+              while (!refine_done.load(std::memory_order_acquire)) {
+                if (abort_helper.load(std::memory_order_acquire)) return;
+                detail::cpu_relax();
+              }
+              wn = b;
+              b *= refine_shrink;
+            }
+            const bool stop = host_step(k, a, b);
+            tested.store(k, std::memory_order_release);
+            if (stop) break;
+          }
+        } catch (...) {
+          helper_error = std::current_exception();
+        }
+        finished.store(true, std::memory_order_release);
+      });
+      std::exception_ptr launch_error;
+      try {
+        size_t enq = 0;
+        while (!finished.load(std::memory_order_acquire)) {
+          const size_t rq = refine_request.load(std::memory_order_acquire);
+          if (rq != 0) {
+            check(llz_krylov_refine(kry, (int64_t)rq, &refine_shrink), "llz_krylov_refine");
+            ++stats_.refinements;
+            enq = rq;  // the iterations enqueued beyond rq used the un-refined vector and were dropped
+            enqueued.store(enq, std::memory_order_release);
+            refine_request.store(0, std::memory_order_relaxed);
+            refine_done.store(true, std::memory_order_release);
+            continue;
+          }
+          const size_t next = tested.load(std::memory_order_acquire) + 1;  // first iteration not tested yet
+          const size_t ahead = std::min(max_iteration, next + depth);
+          if (enq < ahead && enq + 2 <= capacity) {
+            enqueue_step();
+            enqueued.store(++enq, std::memory_order_release);
+          } else if (enq < next && enq < max_iteration) {
+            throw basis_full(enq);  // a needed iteration does not fit
+          } else {
+            detail::cpu_relax();
+          }
+        }
+      } catch (...) {
+        launch_error = std::current_exception();
+        abort_helper.store(true, std::memory_order_release);
+      }
+      helper.join();
+      if (launch_error) std::rethrow_exception(launch_error);
+      if (helper_error) std::rethrow_exception(helper_error);
     }
 
     // :312-319 — Ritz vectors from T_m with the last coupling dropped
