@@ -21,7 +21,7 @@
 
 namespace llz {
 
-constexpr int CT = 8;  // columns per register tile
+constexpr int kCT = 8;  // columns per register tile (16 in the small-n instantiations: more loads in flight per thread)
 
 // ------------------------------------------------------------------------------------------------------------------
 struct ProjectArgs {
@@ -47,7 +47,7 @@ template <class T> __device__ __forceinline__ const T* column_ptr(const void* V,
   return (j < nq) ? reinterpret_cast<const T*>(Q[j]) : reinterpret_cast<const T*>(V) + (int64_t)(j - nq) * ld;
 }
 
-template <class T, int VPT, bool FULL>
+template <class T, int VPT, bool FULL, int CT>
 __device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base, typename Num<T>::R alpha,
                                              typename Num<T>::R beta, double* hs_warp, int lane, double& wnorm2) {
   using R = typename Num<T>::R;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void project_slab(const ProjectArgs& a, int64_t base,
   }
 }
 
-template <class T, int VPT>
+template <class T, int VPT, int CT = kCT>
 __device__ __forceinline__ void project_body(const ProjectArgs& a, double* smem_d) {
   using R = typename Num<T>::R;
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
@@ -164,9 +164,9 @@ __device__ __forceinline__ void project_body(const ProjectArgs& a, double* smem_
   for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
     const int64_t base = s * SLAB;
     if (base + SLAB <= a.n)
-      project_slab<T, VPT, true>(a, base, alpha, beta, hs_warp, lane, wnorm2);
+      project_slab<T, VPT, true, CT>(a, base, alpha, beta, hs_warp, lane, wnorm2);
     else
-      project_slab<T, VPT, false>(a, base, alpha, beta, hs_warp, lane, wnorm2);
+      project_slab<T, VPT, false, CT>(a, base, alpha, beta, hs_warp, lane, wnorm2);
   }
   const double wn = block_sum(wnorm2, scratch);  // also orders the hs writes before the cross-warp sum below
   double* out = a.ph + (size_t)blockIdx.x * (width + 1);
@@ -277,7 +277,7 @@ struct UpdateArgs {
   GatherPush push;   // row-sharded: also store `out` into the peers' exchange buffers (fused all-gather)
 };
 
-template <class T, int VPT, bool FULL>
+template <class T, int VPT, bool FULL, int CT>
 __device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base, const T* cs, typename Num<T>::R alpha,
                                               typename Num<T>::R beta, T h1, T h2) {
   constexpr int VEC = Num<T>::VEC;
@@ -369,7 +369,7 @@ __device__ __forceinline__ double update_slab(const UpdateArgs& a, int64_t base,
   return nrm;
 }
 
-template <class T, int VPT>
+template <class T, int VPT, int CT = kCT>
 __device__ __forceinline__ void update_body(const UpdateArgs& a, unsigned char* smem_u) {
   constexpr int NC = Num<T>::NC, VEC = Num<T>::VEC;
   T* cs = reinterpret_cast<T*>(smem_u);
@@ -404,8 +404,8 @@ __device__ __forceinline__ void update_body(const UpdateArgs& a, unsigned char* 
   double nrm = 0.0;
   for (int64_t s = blockIdx.x; s < nslabs; s += gridDim.x) {
     const int64_t base = s * SLAB;
-    nrm += (base + SLAB <= a.n) ? update_slab<T, VPT, true>(a, base, cs, alpha, beta, h1, h2)
-                                : update_slab<T, VPT, false>(a, base, cs, alpha, beta, h1, h2);
+    nrm += (base + SLAB <= a.n) ? update_slab<T, VPT, true, CT>(a, base, cs, alpha, beta, h1, h2)
+                                : update_slab<T, VPT, false, CT>(a, base, cs, alpha, beta, h1, h2);
   }
   if (a.pb) {
     const double t = block_sum(nrm, scratch);
@@ -517,17 +517,17 @@ __device__ __forceinline__ void grid_barrier(const OrthArgs& a, int index) {
   __syncthreads();
 }
 
-template <class T, int VPT>
+template <class T, int VPT, int CT>
 __global__ void __launch_bounds__(kThreads, 2) k_orth(OrthArgs a) {
   using R = typename Num<T>::R;
   constexpr int VEC = Num<T>::VEC;
   extern __shared__ __align__(16) unsigned char smem_o[];
   __shared__ double scratch[kWarps];
-  project_body<T, VPT>(a.p, reinterpret_cast<double*>(smem_o));
+  project_body<T, VPT, CT>(a.p, reinterpret_cast<double*>(smem_o));
   grid_barrier(a, 1);
   if ((int)blockIdx.x < a.nred) reduce_body(a.r, blockIdx.x, a.nred);
   grid_barrier(a, 2);
-  update_body<T, VPT>(a.u, smem_o);  // (row-sharded: waits for the peers' coefficient messages in its prologue)
+  update_body<T, VPT, CT>(a.u, smem_o);  // (row-sharded: waits for the peers' coefficient messages in its prologue)
   grid_barrier(a, 3);
   const double beta = norm_and_publish(a.s, scratch);
   if (!(beta > 0.0) || !isfinite(beta)) return;
@@ -1023,13 +1023,13 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
 // a full-reorthogonalisation iteration whose columns fit one projection chunk.  *fused = 0 (nothing launched) when the
 // shape does not allow it (too many columns for the shared-memory accumulators, or the grid would not be co-resident).
 // Resident CTAs per SM of k_orth for a given amount of dynamic shared memory (cached: the query costs microseconds).
-template <class T, int VPT> static int orth_ctas_per_sm(size_t smem) {
+template <class T, int VPT, int CT> static int orth_ctas_per_sm(size_t smem) {
   static std::map<size_t, int> cache;
   auto it = cache.find(smem);
   if (it != cache.end()) return it->second;
   int per_sm = 0;
-  if (set_smem(k_orth<T, VPT>, smem) != LLZ_OK) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orth<T, VPT>, kThreads, smem) != cudaSuccess) per_sm = 0;
+  if (set_smem(k_orth<T, VPT, CT>, smem) != LLZ_OK) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_orth<T, VPT, CT>, kThreads, smem) != cudaSuccess) per_sm = 0;
   cache[smem] = per_sm;
   return per_sm;
 }
@@ -1038,17 +1038,17 @@ template <class T> static size_t orth_smem(int total_cols) {
   const size_t need = std::max(((size_t)kWarps * total_cols * Num<T>::NC + kWarps) * sizeof(double), std::max<size_t>(16, (size_t)total_cols * sizeof(T)));
   return (need + 4095) / 4096 * 4096;
 }
-template <class T, int VPT> static int orth_grid(llz_ctx_t ctx, int total_cols, int64_t n) {
-  const int per_sm = orth_ctas_per_sm<T, VPT>(orth_smem<T>(total_cols));
+template <class T, int VPT, int CT> static int orth_grid(llz_ctx_t ctx, int total_cols, int64_t n) {
+  const int per_sm = orth_ctas_per_sm<T, VPT, CT>(orth_smem<T>(total_cols));
   if (per_sm < 1) return 0;
   const int64_t nslabs = (n + slab_rows<T>(VPT) - 1) / slab_rows<T>(VPT);
   const int grid = persistent_grid(ctx, nslabs, std::min(per_sm, 2));
   return (total_cols * Num<T>::NC + 1 + 31) / 32 <= grid ? grid : 0;  // the reduction needs one CTA per 32 values
 }
 
-template <class T, int VPT>
+template <class T, int VPT, int CT>
 static int orth_impl(llz_ctx_t ctx, OrthArgs& a, int* fused, int* grid_out) {
-  const int grid = orth_grid<T, VPT>(ctx, a.p.ncols, a.p.n);
+  const int grid = orth_grid<T, VPT, CT>(ctx, a.p.ncols, a.p.n);
   if (grid < 1) {
     *fused = 0;
     return LLZ_OK;
@@ -1066,20 +1066,24 @@ static int orth_impl(llz_ctx_t ctx, OrthArgs& a, int* fused, int* grid_out) {
   a.bar_base = ctx->bar_count;
   ctx->bar_count += 3ull * (unsigned long long)grid;
   void* params[] = {&a};
-  cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_orth<T, VPT>, dim3((unsigned)grid), dim3(kThreads), params, smem, ctx->stream);
+  cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_orth<T, VPT, CT>, dim3((unsigned)grid), dim3(kThreads), params, smem, ctx->stream);
   if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_orth: %s", cudaGetErrorString(le));
   *fused = 1;
   *grid_out = grid;
   return check_launch(ctx, "k_orth");
 }
 
+// Small problems (one packet per thread, fewer threads than the GPU holds) keep 16 columns of loads in flight per
+// thread instead of 8: there the streaming passes are bound by latency x bytes in flight, not by bandwidth.
+template <class T> constexpr int small_ct() { return sizeof(T) <= 8 ? 16 : kCT; }
+
 bool orth_fusable(llz_ctx_t ctx, int dtype, int total_cols, int64_t n) {
   if (total_cols < 1 || total_cols > max_project_cols(dtype)) return false;
   switch (dtype) {
-    case LLZ_F32: return (pick_vpt<float>(ctx, n) == 2 ? orth_grid<float, 2>(ctx, total_cols, n) : orth_grid<float, 1>(ctx, total_cols, n)) > 0;
-    case LLZ_F64: return (pick_vpt<double>(ctx, n) == 2 ? orth_grid<double, 2>(ctx, total_cols, n) : orth_grid<double, 1>(ctx, total_cols, n)) > 0;
-    case LLZ_C64: return (pick_vpt<float2>(ctx, n) == 2 ? orth_grid<float2, 2>(ctx, total_cols, n) : orth_grid<float2, 1>(ctx, total_cols, n)) > 0;
-    case LLZ_C128: return (pick_vpt<double2>(ctx, n) == 2 ? orth_grid<double2, 2>(ctx, total_cols, n) : orth_grid<double2, 1>(ctx, total_cols, n)) > 0;
+    case LLZ_F32: return (pick_vpt<float>(ctx, n) == 2 ? orth_grid<float, 2, kCT>(ctx, total_cols, n) : orth_grid<float, 1, small_ct<float>()>(ctx, total_cols, n)) > 0;
+    case LLZ_F64: return (pick_vpt<double>(ctx, n) == 2 ? orth_grid<double, 2, kCT>(ctx, total_cols, n) : orth_grid<double, 1, small_ct<double>()>(ctx, total_cols, n)) > 0;
+    case LLZ_C64: return (pick_vpt<float2>(ctx, n) == 2 ? orth_grid<float2, 2, kCT>(ctx, total_cols, n) : orth_grid<float2, 1, small_ct<float2>()>(ctx, total_cols, n)) > 0;
+    case LLZ_C128: return (pick_vpt<double2>(ctx, n) == 2 ? orth_grid<double2, 2, kCT>(ctx, total_cols, n) : orth_grid<double2, 1, small_ct<double2>()>(ctx, total_cols, n)) > 0;
   }
   return false;
 }
@@ -1100,8 +1104,8 @@ int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t 
   a.s.npb = 0;
   a.s.sink = sink;
   LLZ_DISPATCH(dtype, {
-    if (pick_vpt<T>(ctx, n) == 2) return orth_impl<T, 2>(ctx, a, fused, grid_out);
-    return orth_impl<T, 1>(ctx, a, fused, grid_out);
+    if (pick_vpt<T>(ctx, n) == 2) return orth_impl<T, 2, kCT>(ctx, a, fused, grid_out);
+    return orth_impl<T, 1, small_ct<T>()>(ctx, a, fused, grid_out);
   });
   return LLZ_OK;
 }

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) k_sell_fill(const IDX* __restrict__ 
 // Each warp walks TWO adjacent slices per step (64 rows: 2 x 5 x 384 B of matrix data in flight per warp on a 5-point
 // stencil) and fetches the slice pointers of its next step before it starts on the current one, so the three dependent
 // round trips (slice pointer -> column/value -> x gather) of consecutive steps overlap.
-template <class T, int MINB>
+template <class T, int MINB, int Q = 4>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
                     const int32_t* __restrict__ perm, const T* __restrict__ x, const T* halo, int32_t nloc,
@@ -255,13 +255,13 @@ __global__ void __launch_bounds__(kThreads, MINB)
 #pragma unroll
     for (int u = 0; u < U; ++u) sum[u] = zero_of(T());
     const int wmax = max(w[0], w[1]);
-    for (int j = 0; j < wmax; j += 4) {
-      int32_t c[U][4];
-      T v[U][4], xv[U][4];
+    for (int j = 0; j < wmax; j += Q) {  // Q entries per row in flight (8 when the whole matrix is one step of the grid)
+      int32_t c[U][Q];
+      T v[U][Q], xv[U][Q];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < Q; ++q) {
           const bool in = j + q < w[u];
           const int64_t at = p0[u] + (int64_t)(j + q) * kSellC + lane;
           c[u][q] = in ? __ldg(scol + at) : -1;
@@ -270,11 +270,11 @@ __global__ void __launch_bounds__(kThreads, MINB)
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xv[u][q] = c[u][q] >= 0 ? gather_x(x, halo, c[u][q], nloc) : zero_of(T());
+        for (int q = 0; q < Q; ++q) xv[u][q] = c[u][q] >= 0 ? gather_x(x, halo, c[u][q], nloc) : zero_of(T());
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < Q; ++q)
           if (c[u][q] >= 0) sum[u] = add_rn(sum[u], mul_rn(v[u][q], xv[u][q]));
     }
 #pragma unroll
@@ -611,7 +611,12 @@ template <class T> struct CsrOp : OpBase {
     static const int env_blocks = getenv("LLZ_SELL_BLOCKS") ? atoi(getenv("LLZ_SELL_BLOCKS")) : 0;
     const int blocks = env_blocks ? env_blocks : (Num<T>::NC == 1 ? 4 : 3);
     cudaError_t e;
-    if (blocks >= 4)
+    if (g * per_cta >= n_slices && (int64_t)g <= (int64_t)ctx->num_sms * 2)
+      // small matrix: every warp has at most one step and the grid does not fill the GPU — latency-bound, so keep
+      // twice the entries per row in flight (the registers that costs do not limit occupancy here)
+      e = launch_chain(ctx, k_sell_spmv_dot<T, 2, 8>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
+                       (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
+    else if (blocks >= 4)
       e = launch_chain(ctx, k_sell_spmv_dot<T, 4>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
                        (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     else
