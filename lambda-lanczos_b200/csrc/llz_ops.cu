@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) k_sell_fill(const IDX* __restrict__ 
 // Each warp walks TWO adjacent slices per step (64 rows: 2 x 5 x 384 B of matrix data in flight per warp on a 5-point
 // stencil) and fetches the slice pointers of its next step before it starts on the current one, so the three dependent
 // round trips (slice pointer -> column/value -> x gather) of consecutive steps overlap.
-template <class T, int MINB, int Q = 4>
+template <class T, int MINB, int Q = 4, int U = 2>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_sell_spmv_dot(const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ scol, const T* __restrict__ sval,
                     const int32_t* __restrict__ perm, const T* __restrict__ x, const T* halo, int32_t nloc,
@@ -230,7 +230,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
                     PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
-  constexpr int U = 2;  // slices per warp step
   const int lane = threadIdx.x & 31;
   double dot = 0.0;
   const int64_t stride = (int64_t)gridDim.x * kWarps * U;
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
     T sum[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) sum[u] = zero_of(T());
-    const int wmax = max(w[0], w[1]);
+    const int wmax = U == 2 ? max(w[0], w[U - 1]) : w[0];
     for (int j = 0; j < wmax; j += Q) {  // Q entries per row in flight (8 when the whole matrix is one step of the grid)
       int32_t c[U][Q];
       T v[U][Q], xv[U][Q];
@@ -611,12 +610,14 @@ template <class T> struct CsrOp : OpBase {
     static const int env_blocks = getenv("LLZ_SELL_BLOCKS") ? atoi(getenv("LLZ_SELL_BLOCKS")) : 0;
     const int blocks = env_blocks ? env_blocks : (Num<T>::NC == 1 ? 4 : 3);
     cudaError_t e;
-    if (g * per_cta >= n_slices && (int64_t)g <= (int64_t)ctx->num_sms * 2)
-      // small matrix: every warp has at most one step and the grid does not fill the GPU — latency-bound, so keep
-      // twice the entries per row in flight (the registers that costs do not limit occupancy here)
-      e = launch_chain(ctx, k_sell_spmv_dot<T, 2, 8>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
+    if (g * per_cta >= n_slices && (int64_t)g <= (int64_t)ctx->num_sms * 2) {
+      // small matrix: every warp has at most one step and the grid does not fill the GPU — latency-bound, so one slice
+      // per warp (twice the warps) with twice the entries per row in flight (the registers that costs do not limit
+      // occupancy here)
+      g = std::max<int64_t>(1, (n_slices + kWarps - 1) / kWarps);
+      e = launch_chain(ctx, k_sell_spmv_dot<T, 2, 8, 1>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
                        (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
-    else if (blocks >= 4)
+    } else if (blocks >= 4)
       e = launch_chain(ctx, k_sell_spmv_dot<T, 4>, (int)g, kThreads, 0, d_slice_ptr, d_scol, d_sval, d_perm, (const T*)x, cur_halo, nloc32(),
                        (T*)y, n_local, n_slices, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
     else
