@@ -308,9 +308,8 @@ class LambdaLanczos {
               wn = b;
               b *= refine_shrink;
             }
-            const bool stop = host_step(k, a, b);
+            if (host_step(k, a, b)) break;  // (not published as tested: the launcher must not run further ahead)
             tested.store(k, std::memory_order_release);
-            if (stop) break;
           }
         } catch (...) {
           helper_error = std::current_exception();
@@ -318,11 +317,24 @@ class LambdaLanczos {
         finished.store(true, std::memory_order_release);
       });
       std::exception_ptr launch_error;
+      // Row-sharded runs replicate this control flow on every rank, and the kernels of an enqueued iteration wait for
+      // the peers' messages of that iteration: wherever the ranks take a decision together (refinement, end of the
+      // run) every rank must have enqueued the SAME iterations, whatever its threads' timing was — exactly `depth`
+      // beyond the iteration the decision is about.
+      const bool lockstep = ctx.nranks() > 1;
       try {
         size_t enq = 0;
+        auto top_up = [&](size_t decided) {
+          const size_t target = std::min(max_iteration, decided + depth);
+          while (lockstep && enq < target && enq + 2 <= capacity) {
+            enqueue_step();
+            enqueued.store(++enq, std::memory_order_release);
+          }
+        };
         while (!finished.load(std::memory_order_acquire)) {
           const size_t rq = refine_request.load(std::memory_order_acquire);
           if (rq != 0) {
+            top_up(rq);
             check(llz_krylov_refine(kry, (int64_t)rq, &refine_shrink), "llz_krylov_refine");
             ++stats_.refinements;
             enq = rq;  // the iterations enqueued beyond rq used the un-refined vector and were dropped
@@ -342,6 +354,7 @@ class LambdaLanczos {
             detail::cpu_relax();
           }
         }
+        if (!helper_error) top_up(itern);
       } catch (...) {
         launch_error = std::current_exception();
         abort_helper.store(true, std::memory_order_release);

@@ -163,6 +163,17 @@ def run_gpu(rank, world):
         y_local = op.matvec(x[row0:row0 + nl])
         y_ref = pkg.Operator.csr(solo, *full).matvec(x)
         assert np.array_equal(y_local, y_ref[row0:row0 + nl]), name  # same summation order per row: bit-identical
+    # the same for SELL-32-sigma storage (what bench.py runs row-sharded at every N): unsorted and window-sorted slices
+    for name, full, dtype in (("laplacian", wl.laplacian2d_csr(61, 47), np.float64), ("random", wl.random_symmetric_csr(3001, 8), np.float64),
+                              ("peierls", wl.peierls_csr(24, 20), np.complex128), ("random c64", wl.random_symmetric_csr(2000, 5, dtype=np.complex64), np.complex64)):
+        n = full[0].size - 1
+        row0, nl = wl.partition(n, rank, world)
+        x = wl.start_vector(n, dtype, seed=4)
+        y_ref = pkg.Operator.csr(solo, *full).matvec(x)
+        for sigma in (1, 64, 0):
+            op = pkg.Operator.sell(ctx, *wl.csr_row_block(*full, row0, nl), row0=row0, n_cols=n, sigma=sigma)
+            assert (op.n, op.n_global, op.row0) == (nl, n, row0)
+            assert np.array_equal(op.matvec(x[row0:row0 + nl]), y_ref[row0:row0 + nl]), (name, sigma)
     for L, dtype in ((12, np.float64), (14, np.complex128)):
         opx = pkg.Operator.xxz(ctx, L, dtype=dtype)
         n = opx.n_global
@@ -201,6 +212,36 @@ def run_gpu(rank, world):
             assert res < max(10 * res_ref, 1e-9), (name, i, res, res_ref)
         if rank == 0:
             print(f"  {name}: iterations sharded {eng.getIterationCounts()} single {ref.getIterationCounts()} eigenvalues {ev}", flush=True)
+
+    # ---- 2b. row-sharded SELL Lanczos runs against the ORACLE (the compiled reference where it travelled, else the C
+    #          restatement): eigenvalues 1e-10, overlap 1-1e-9, iteration counts side by side ----
+    import oracle
+
+    chk = oracle.best()
+    for name, full, find_max, k in (("random max (sell)", wl.random_symmetric_csr(20000, 8), True, 1),
+                                    ("laplacian 3 smallest (sell)", wl.laplacian2d_csr(40, 37), False, 3),
+                                    ("peierls 2 lowest (sell)", wl.peierls_csr(20, 20, flux=0.05, trap=0.3), False, 2)):
+        n = full[0].size - 1
+        dtype = full[2].dtype
+        row0, nl = wl.partition(n, rank, world)
+        start = wl.start_vector(n, dtype)
+        eng = pkg.LambdaLanczos(pkg.Operator.sell(ctx, *wl.csr_row_block(*full, row0, nl), row0=row0, n_cols=n), n, find_max, k)
+        eng.init_vector = start[row0:row0 + nl]
+        ev, vec = eng.run()
+        ref = chk.lanczos(*full, find_max=find_max, num_eigs=k, init=start)
+        assert np.allclose(ev, ref.eigenvalues[:k], rtol=1e-10, atol=1e-12), (name, ev, ref.eigenvalues)
+        for i in range(k):
+            g = gather_blocks(dist, torch, np.ascontiguousarray(vec[i]), world, sizes_of(n))
+            degenerate = any(abs(ref.eigenvalues[i] - ref.eigenvalues[j]) < 1e-9 * max(1, abs(ref.eigenvalues[i])) for j in range(k) if j != i)
+            if not degenerate:
+                assert 1 - abs(np.vdot(ref.eigenvectors[i], g)) < 1e-9, (name, i)
+            res = np.linalg.norm(wl.csr_matvec(*full, g) - ev[i] * g)
+            res_ref = np.linalg.norm(wl.csr_matvec(*full, ref.eigenvectors[i]) - ref.eigenvalues[i] * ref.eigenvectors[i])
+            assert res < max(10 * res_ref, 1e-9), (name, i, res, res_ref)
+        assert len(eng.getIterationCounts()) == len(ref.iter_counts)
+        assert all(abs(a - b) <= 3 for a, b in zip(eng.getIterationCounts(), ref.iter_counts)), (eng.getIterationCounts(), ref.iter_counts)
+        if rank == 0:
+            print(f"  {name}: iterations sharded {eng.getIterationCounts()} {chk.kind} {ref.iter_counts} eigenvalues {ev}", flush=True)
 
     # ---- 3. XXZ ground state (config 4 at small L) and Exponentiator (config 5) on row blocks ----
     L = 16
