@@ -272,6 +272,8 @@ struct UpdateArgs {
   const void* u1;           // basis columns k-1 and k-2; their projection coefficients sit at coef[cu1], coef[cu2]
   const void* u2;
   int cu1, cu2;
+  double* wnorm_out;  // row-sharded: receives element wnorm_index of the coefficient message (||w'||^2), if non-null
+  int wnorm_index;
   PeerMsg coef_msg;  // row-sharded: coefficients = sum over ranks of this message (element col*NC + c)
   PeerMsg norm_msg;  // row-sharded: deliver sum(pb) group-wide from the last CTA
   GatherPush push;   // row-sharded: also store `out` into the peers' exchange buffers (fused all-gather)
@@ -377,6 +379,8 @@ __device__ __forceinline__ void update_body(const UpdateArgs& a, unsigned char* 
   const int tid = threadIdx.x;
   const bool peer = a.coef_msg.ch.G > 0;
   if (peer) peer_wait(a.coef_msg.ch, a.coef_msg.seq);
+  if (peer && a.wnorm_out && a.wnorm_index >= 0 && blockIdx.x == 0 && tid == 0)
+    *a.wnorm_out = peer_sum(a.coef_msg.ch, a.coef_msg.seq, a.wnorm_index);
   auto coef_at = [&](int col) -> T {
     if (peer) {
       const double re = peer_sum(a.coef_msg.ch, a.coef_msg.seq, col * NC);
@@ -447,8 +451,7 @@ __device__ __forceinline__ double norm_and_publish(const ScaleNormArgs& a, doubl
     if (a.sink.h_alpha && a.sink.alpha_in) *a.sink.h_alpha = __ldcg(a.sink.alpha_in);
     if (a.sink.h_wnorm) {
       double wn = beta;
-      if (a.sink.wnorm_msg.ch.G > 0) wn = sqrt(peer_sum(a.sink.wnorm_msg.ch, a.sink.wnorm_msg.seq, a.sink.wnorm_index));
-      else if (a.sink.wnorm2_in) wn = sqrt(__ldcg(a.sink.wnorm2_in));
+      if (a.sink.wnorm2_in) wn = sqrt(__ldcg(a.sink.wnorm2_in));
       *a.sink.h_wnorm = wn;
     }
     if (a.sink.h_flag) {
@@ -991,6 +994,8 @@ static int make_update_args(int dtype, const ColumnSet& cs, int col0, int ncols,
   a.n = n;
   a.coef = coef;
   a.coef_msg = coef_msg;
+  a.wnorm_out = fold.wnorm_out;
+  a.wnorm_index = fold.wnorm_index;
   a.norm_msg = norm_partials ? norm_msg : PeerMsg();
   a.push = (norm_partials && a.norm_msg.ch.G > 0) ? fold.push : GatherPush();
   a.pb = norm_partials;

@@ -171,8 +171,7 @@ int allreduce_scalar(llz_ctx_t ctx, double* partials, int* count) {
 // One classical Gram-Schmidt pass of `w` against cs: project -> reduce -> update (in place).  With an empty column
 // set only the update kernel runs (it then just produces the norm partials of w).  `wnorm` tells the caller where
 // ||w'||^2 of this pass can be read (peer message element or kry->d_misc[1]).
-int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, bool want_norm, int* norm_grid,
-             PeerMsg* wnorm_msg = nullptr, int* wnorm_index = nullptr) {
+int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, bool want_norm, int* norm_grid) {
   // (row-sharded with peer channels: fold.norm_msg, if used, is delivered by the update kernel that writes the norm
   //  partials; the coefficients travel as one message of the coefficient channel)
   llz_ctx_t ctx = kry->ctx;
@@ -180,14 +179,10 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
   const int total = cs.ncols();
   const int max_grid = std::min(kMaxGrid, ctx->num_sms * 2);
   PeerMsg coef_msg;  // row-sharded with peer channels: the coefficients travel as one message
-  if (wnorm_msg) *wnorm_msg = PeerMsg();
+  bool peer = false;
   if (total > 0) {
-    const bool peer = comm_p2p(ctx) && total * nc + 1 <= comm_coef_capacity(ctx);
-    if (peer) {
-      coef_msg = comm_next_message(ctx, kChanCoef);
-      if (wnorm_msg) *wnorm_msg = coef_msg;
-      if (wnorm_index) *wnorm_index = total * nc;
-    }
+    peer = comm_p2p(ctx) && total * nc + 1 <= comm_coef_capacity(ctx);
+    if (peer) coef_msg = comm_next_message(ctx, kChanCoef);
     const int pchunk = max_project_cols(kry->dtype);
     for (int c0 = 0; c0 < total; c0 += pchunk) {
       const int cols = std::min(pchunk, total - c0);
@@ -218,6 +213,10 @@ int cgs_pass(llz_krylov_t kry, const ColumnSet& cs, void* w, const Fold& fold, b
     const int cols = std::min(uchunk, generic - c0);
     const bool last = c0 + cols >= generic;
     Fold f = (c0 == 0) ? fold : Fold();
+    if (c0 == 0 && peer) {  // ||w'||^2 travelled with the coefficients: keep a local copy (kry->d_misc[1], as on one rank)
+      f.wnorm_out = kry->d_misc + 1;
+      f.wnorm_index = total * nc;
+    }
     f.norm_msg = fold.norm_msg;
     f.push = fold.push;  // (launch_update only honours it in the chunk that writes the final vector and its norm)
     ProfScope ps(ctx, "update", (double)kry->n * (double)dtype_size(kry->dtype) * (cols + f.mode + 2));
@@ -533,8 +532,8 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
       PeerMsg coef_msg;
       if (peer) {
         coef_msg = comm_next_message(ctx, kChanCoef);
-        sink.wnorm_msg = coef_msg;
-        sink.wnorm_index = total * nc;
+        fold.wnorm_out = kry->d_misc + 1;
+        fold.wnorm_index = total * nc;
       }
       sink.beta_out = kry->d_beta + (k - 1);
       sink.alpha_in = kry->d_alpha + (k - 1);
@@ -553,7 +552,7 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
       kry->k = k;
       return LLZ_OK;
     }
-    LLZ_TRY(cgs_pass(kry, cs, y, fold, orth != LLZ_ORTH_FULL_TWICE, &grid, &sink.wnorm_msg, &sink.wnorm_index));
+    LLZ_TRY(cgs_pass(kry, cs, y, fold, orth != LLZ_ORTH_FULL_TWICE, &grid));
     if (orth == LLZ_ORTH_FULL_TWICE) {
       Fold nofold;
       nofold.norm_msg = sink.beta_msg;

@@ -46,6 +46,9 @@ struct Fold {
                                         // also delivers their sum as this message (consumed by scale_by_norm)
   GatherPush push;                      // row-sharded: ... and stores the vector it writes into the peers' exchange
                                         // buffers (fused all-gather for operators that read the whole input vector)
+  double* wnorm_out = nullptr;          // row-sharded with peer channels: the update kernel — which waits for the
+  int wnorm_index = -1;                 // coefficient message — copies element wnorm_index of it (||w'||^2) here, so
+                                        // that no later kernel has to read a message slot a fast peer may already reuse
 };
 
 // Where scale_by_norm publishes the iteration's scalars.
@@ -59,8 +62,6 @@ struct ScalarSink {
   long long* h_flag = nullptr;    // mapped pinned: set to `flag_value` after the scalars are visible
   long long flag_value = 0;
   PeerMsg beta_msg;               // row-sharded: ||u||^2 = sum over ranks of this message instead of the partials
-  PeerMsg wnorm_msg;              // row-sharded: ||w'||^2 = element wnorm_index of this (already awaited) message
-  int wnorm_index = 0;
 };
 
 int max_project_cols(int dtype);  // columns one projection launch can accumulate in shared memory

@@ -36,6 +36,12 @@ template <class T> __device__ __forceinline__ T gather_x(const T* __restrict__ x
   return (c < nloc) ? __ldg(x + c) : __ldcg(halo + (c - nloc));
 }
 
+// *bad = 1 if any column index lies outside [0, n_cols)
+__global__ void __launch_bounds__(kThreads) k_col_range(const int32_t* __restrict__ col, int64_t count, int32_t n_cols, int* bad) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads)
+    if (col[i] < 0 || col[i] >= n_cols) *bad = 1;
+}
+
 // sendbuf[i] = x[idx[i]]: the entries of the local block the peers asked for, grouped by peer.
 template <class T> __global__ void __launch_bounds__(kThreads) k_pack(const T* __restrict__ x, const int32_t* __restrict__ idx, T* __restrict__ out, int64_t count) {
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads) out[i] = __ldg(x + idx[i]);
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 4)
   extern __shared__ __align__(16) unsigned char smem_s[];
   if (halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
   T* prod = reinterpret_cast<T*>(smem_s);
-  IDX* rp = reinterpret_cast<IDX*>(prod + cap);
+  IDX* rp = reinterpret_cast<IDX*>(smem_s + ((size_t)cap * sizeof(T) + 15) / 16 * 16);  // (8-byte row pointers after an odd count of floats)
   __shared__ double scratch[kWarps];
   const int tid = threadIdx.x;
   double dot = 0.0;
@@ -569,7 +575,7 @@ template <class T> struct CsrOp : OpBase {
   }
 
   template <class IDX> int launch_stream(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
-    const size_t smem = (size_t)stream_cap * sizeof(T) + (size_t)(stream_rows + 1) * sizeof(IDX);
+    const size_t smem = ((size_t)stream_cap * sizeof(T) + 15) / 16 * 16 + (size_t)(stream_rows + 1) * sizeof(IDX);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k_csr_stream_dot<T, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -884,9 +890,18 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
     return s;
   }
   const int64_t first = rowptr[0], last = rowptr[n_rows];
-  if (first != 0 || last < 0) {
+  bool monotone = first == 0 && last >= 0;
+  for (int64_t i = 0; monotone && i < n_rows; ++i) monotone = rowptr[i + 1] >= rowptr[i];
+  if (!monotone) {
     delete op;
     return fail(LLZ_ERR_INVALID, "csr: rowptr must start at 0 (got %lld) and be non-decreasing", (long long)first);
+  }
+  if (host_arrays && ctx->nranks == 1) {  // (row-sharded: llz_halo_plan range-checks the columns; device arrays: k_col_range below)
+    for (int64_t p = 0; p < last; ++p)
+      if (colidx_in[p] < 0 || colidx_in[p] >= n_cols) {
+        delete op;
+        return fail(LLZ_ERR_INVALID, "csr: column index %d at position %lld outside [0, %lld)", (int)colidx_in[p], (long long)p, (long long)n_cols);
+      }
   }
   op->nnz = last;
   op->idx32 = last < (int64_t)0x7fffffff;
@@ -929,6 +944,16 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
       guard(dev_malloc(ctx, &op->d_rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)), "rowptr alloc");
       if (s == LLZ_OK) guard(cudaMemcpyAsync(op->d_rowptr, rowptr, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice, ctx->stream), "rowptr copy");
     }
+  }
+  if (s == LLZ_OK && !host_arrays && ctx->nranks == 1 && last > 0) {  // device arrays: range-check the columns on the device
+    int* d_bad = reinterpret_cast<int*>(ctx->d_result);
+    guard(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream), "memset");
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>((last + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 8));
+    k_col_range<<<g, kThreads, 0, ctx->stream>>>(op->d_colidx, last, (int32_t)std::min<int64_t>(n_cols, 0x7fffffff), d_bad);
+    int bad = 0;
+    guard(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "copy");
+    guard(cudaStreamSynchronize(ctx->stream), "sync");
+    if (s == LLZ_OK && bad) s = fail(LLZ_ERR_INVALID, "csr: a column index lies outside [0, %lld)", (long long)n_cols);
   }
   if (s == LLZ_OK) guard(cudaStreamSynchronize(ctx->stream), "sync");
   if (s != LLZ_OK) {
