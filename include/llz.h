@@ -139,6 +139,10 @@ int llz_op_rows(llz_op_t op, int64_t* n_local);
 /* Local rows, rows of the whole operator and first global row of the local block (n_global = n_local, row0 = 0 for a
  * single rank).  The reference's `matrix_size` (lambda_lanczos.hpp:136) is n_global. */
 int llz_op_shape(llz_op_t op, int64_t* n_local, int64_t* n_global, int64_t* row0);
+/* How the operator is held on the device: "DIA", "SELL-32", "SELL-32-sigma (sorted windows)", "CSR (stream kernel)",
+ * "XXZ matrix-free (block kernel)", "user callback" ... (static string; "" for a null handle).  llz_op_create_sell with
+ * sigma = 0 picks DIA for operators whose non-zeros lie on at most 16 diagonals, else SELL. */
+const char* llz_op_storage(llz_op_t op);
 /* Algorithmic bytes one apply has to move for the operator itself (A_bytes of SURVEY.md §8d; 0 for matrix-free). */
 int llz_op_bytes(llz_op_t op, int64_t* bytes);
 /* Gerschgorin radius max_i sum_j |a_ij| of the whole operator (group-wide for row-sharded operators): every eigenvalue

@@ -207,6 +207,12 @@ class Operator:
         _check(lib().llz_op_gerschgorin_radius(self.h, C.byref(r)), "llz_op_gerschgorin_radius")
         return float(r.value)
 
+    def storage(self) -> str:
+        """How the operator is held on the device (llz_op_storage): 'DIA', 'SELL-32', 'CSR (stream kernel)', ..."""
+        f = lib().llz_op_storage
+        f.restype = C.c_char_p
+        return f(self.h).decode()
+
     def apply(self, x: "Vector", y: "Vector"):
         _check(lib().llz_op_apply(self.h, x.h, y.h), "llz_op_apply")
 

@@ -113,6 +113,7 @@ struct OpBase {
   int64_t row0 = 0;      // first global row of the local block
   int64_t bytes = 0;
   virtual ~OpBase() {}
+  virtual const char* storage() const { return "operator"; }  // how the operator is held on the device (llz_op_storage)
   // Row-sharded operators: make the remote entries of x that the local rows reference available (halo exchange /
   // all-gather over NCCL, enqueued on ctx->stream).  Called once before every apply_fused.
   virtual int prepare(const void* x) {

@@ -430,6 +430,88 @@ __global__ void __launch_bounds__(kThreads, 2)
   finish_scalar(t, pa, msg, scratch);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// DIA storage for stencil / lattice operators (2-D Laplacian, tight-binding models ...): when every non-zero sits on one
+// of a few diagonals (column - row constant), the matrix is re-stored diagonal by diagonal — vals[d][row], no column
+// indices — so a row reads its products' operands at x[row + offset_d]: contiguous, perfectly coalesced streams instead
+// of dependent gathers, and A_bytes drops from nnz*(s+4) to ndiag*n*s + 2n (a 16-bit presence mask per row: absent
+// entries — grid boundaries — are skipped, never multiplied as zeros).  Products are added in ascending column order
+// with separate multiply and add: y is bit-identical to the CSR / SELL kernels'.  Row-sharded, offsets that leave the
+// block read the halo buffer, which for such operators is the contiguous range of rows just below and just above.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDiaMax = 16;
+struct DiaOffsets {
+  int nd = 0;
+  int off[kDiaMax] = {};  // ascending
+};
+
+// One thread per row: scatter the CSR entries of the row into their diagonals.  *bad is raised if an entry is not on a
+// listed diagonal or the row is not sorted by column (the DIA kernel adds in ascending-column order).
+template <class T, class IDX>
+__global__ void __launch_bounds__(kThreads) k_dia_fill(const IDX* __restrict__ rowptr, const int32_t* __restrict__ colidx, const T* __restrict__ vals,
+                                                       int64_t n, int32_t n_lo, DiaOffsets offs, int64_t ldv, T* __restrict__ dvals,
+                                                       uint16_t* __restrict__ mask, int* bad) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    uint32_t m = 0;
+    int last = -1;
+    for (IDX p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+      const int64_t c = colidx[p];
+      // extended index: own rows [0, n), the halo rows below the block at [-n_lo, 0), those above at [n, ...)
+      const int64_t e = c < n ? c : (c - n < n_lo ? c - n - n_lo : n + (c - n - n_lo));
+      const int64_t off = e - i;
+      int d = -1;
+      for (int q = 0; q < offs.nd; ++q)
+        if (offs.off[q] == off) d = q;
+      if (d < 0 || d <= last) {
+        *bad = 1;
+        continue;
+      }
+      last = d;
+      dvals[(int64_t)d * ldv + i] = vals[p];
+      m |= 1u << d;
+    }
+    mask[i] = (uint16_t)m;
+  }
+}
+
+template <class T, int ND, bool SHARDED>
+__global__ void __launch_bounds__(kThreads, 4)
+    k_dia_spmv_dot(const T* __restrict__ dvals, int64_t ldv, const uint16_t* __restrict__ mask, DiaOffsets offs, const T* __restrict__ x,
+                   const T* halo, int32_t n_lo, T* __restrict__ y, int64_t n, typename Num<T>::R sigma, double* pa, PeerMsg msg,
+                   PeerMsg halo_msg) {
+  __shared__ double scratch[kWarps];
+  if (SHARDED && halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
+  double dot = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const uint32_t m = mask[i];
+    T a[ND], xv[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const bool on = d < offs.nd && ((m >> d) & 1u);
+      a[d] = on ? __ldg(dvals + (int64_t)d * ldv + i) : zero_of(T());
+      if (on) {
+        const int64_t e = i + offs.off[d];
+        if (!SHARDED || (e >= 0 && e < n))
+          xv[d] = __ldg(x + e);
+        else
+          xv[d] = __ldcg(halo + (e < 0 ? n_lo + e : n_lo + (e - n)));  // written by the peers: coherent load
+      } else {
+        xv[d] = zero_of(T());
+      }
+    }
+    T sum = zero_of(T());
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      if (d < offs.nd && ((m >> d) & 1u)) sum = add_rn(sum, mul_rn(a[d], xv[d]));
+    const T xi = x[i];
+    const T yi = add_t(sum, scale_real(xi, sigma));
+    y[i] = yi;
+    dot += re_conj_mul(xi, yi);
+  }
+  const double t = block_sum(dot, scratch);
+  finish_scalar(t, pa, msg, scratch);
+}
+
 // Gerschgorin radius: per-CTA maximum of the absolute row sums (CSR: one thread per row; SELL: one lane per row).
 template <class T, class IDX>
 __global__ void __launch_bounds__(kThreads) k_csr_rowsum_max(const IDX* __restrict__ rowptr, const T* __restrict__ vals, int64_t n, double* out) {
@@ -458,6 +540,24 @@ __global__ void __launch_bounds__(kThreads) k_sell_rowsum_max(const int64_t* __r
     const int w = (int)((slice_ptr[s + 1] - p0) / kSellC);
     double t = 0.0;
     for (int j = 0; j < w; ++j) t += abs1(sval[p0 + (int64_t)j * kSellC + lane]);  // padding holds zeros
+    m = fmax(m, t);
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_dia_rowsum_max(const T* __restrict__ dvals, int64_t ldv, int nd, int64_t n, double* out) {
+  __shared__ double red[kThreads];
+  double m = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    double t = 0.0;
+    for (int d = 0; d < nd; ++d) t += abs1(dvals[(int64_t)d * ldv + r]);  // absent entries hold zeros
     m = fmax(m, t);
   }
   red[threadIdx.x] = m;
@@ -501,12 +601,22 @@ template <class T> struct CsrOp : OpBase {
   int32_t* d_perm = nullptr;  // null when rows are not sorted (sigma = 1)
   int tma_cap = 0;            // > 0: entries per shared-memory stage of the TMA-streamed kernel; 0: register-staged kernel
   int tma_stages = 0;
+  // DIA storage (convert_to_dia releases the CSR arrays)
+  bool dia = false;
+  DiaOffsets dia_offs;
+  int64_t dia_ld = 0;
+  T* d_dvals = nullptr;
+  uint16_t* d_dmask = nullptr;
+  int32_t halo_lo = 0;        // row-sharded: halo entries that lie below the block ...
+  bool halo_contiguous = true;  // ... and whether the halo is exactly the rows just below and just above the block
 
   ~CsrOp() override {
     if (d_slice_ptr) dev_free(ctx, d_slice_ptr);
     if (d_scol) dev_free(ctx, d_scol);
     if (d_sval) dev_free(ctx, d_sval);
     if (d_perm) dev_free(ctx, d_perm);
+    if (d_dvals) dev_free(ctx, d_dvals);
+    if (d_dmask) dev_free(ctx, d_dmask);
     if (d_rowptr) dev_free(ctx, d_rowptr);
     if (d_colidx) dev_free(ctx, d_colidx);
     if (d_vals) dev_free(ctx, d_vals);
@@ -516,6 +626,11 @@ template <class T> struct CsrOp : OpBase {
     if (d_send_idx) dev_free(ctx, d_send_idx);
   }
   int32_t nloc32() const { return (int32_t)std::min<int64_t>(n_local, 0x7fffffff); }
+  const char* storage() const override {
+    if (dia) return "DIA";
+    if (sell) return d_perm ? "SELL-32-sigma (sorted windows)" : "SELL-32";
+    return stream_rows > 0 ? "CSR (stream kernel)" : "CSR (lanes-per-row kernel)";
+  }
 
   // Bring the remote entries of x this block references into d_halo (no-op for a single rank).
   int prepare(const void* x) override {
@@ -635,6 +750,104 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
 
+  template <int ND> int launch_dia_nd(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
+    int64_t g = std::min<int64_t>((n_local + kThreads - 1) / kThreads, std::min<int64_t>(kMaxGrid, (int64_t)ctx->num_sms * 8));
+    if (g < 1) g = 1;
+    cudaError_t e;
+    if (ctx->nranks > 1)
+      e = launch_chain(ctx, k_dia_spmv_dot<T, ND, true>, (int)g, kThreads, 0, (const T*)d_dvals, dia_ld, (const uint16_t*)d_dmask, dia_offs,
+                       (const T*)x, cur_halo, halo_lo, (T*)y, n_local, (typename Num<T>::R)sigma, pa, msg, cur_halo_msg);
+    else
+      e = launch_chain(ctx, k_dia_spmv_dot<T, ND, false>, (int)g, kThreads, 0, (const T*)d_dvals, dia_ld, (const uint16_t*)d_dmask, dia_offs,
+                       (const T*)x, (const T*)nullptr, 0, (T*)y, n_local, (typename Num<T>::R)sigma, pa, msg, PeerMsg());
+    *npa = (int)g;
+    if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_dia_spmv_dot: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return LLZ_OK;
+  }
+  int launch_dia(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
+    return dia_offs.nd <= 8 ? launch_dia_nd<8>(x, y, sigma, pa, npa, msg) : launch_dia_nd<16>(x, y, sigma, pa, npa, msg);
+  }
+
+  // Re-store the uploaded CSR arrays diagonal by diagonal when (almost) every non-zero sits on one of at most 16
+  // diagonals.  The candidate offsets come from a sample of rows (host); the device fill kernel verifies that EVERY
+  // entry is on one of them and that rows are sorted by column, else the CSR arrays are kept (*done = false).
+  // `rowptr` / `col_local`: host copies (columns in the local extended numbering when row-sharded).
+  template <class IDX> int convert_to_dia(const int64_t* rowptr, const int32_t* col_local, bool* done) {
+    *done = false;
+    const int64_t n = n_local;
+    if (n < 1 || nnz < 1 || (ctx->nranks > 1 && !halo_contiguous) || n + (int64_t)halo_lo + (n_halo - halo_lo) >= 0x7fffffff) return LLZ_OK;
+    const int64_t n_hi = n_halo - halo_lo;
+    std::vector<int64_t> offsets;
+    auto scan_row = [&](int64_t i) -> bool {
+      for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+        const int64_t c = col_local[p];
+        const int64_t e = c < n ? c : (c - n < halo_lo ? c - n - halo_lo : n + (c - n - halo_lo));
+        const int64_t off = e - i;
+        if (std::find(offsets.begin(), offsets.end(), off) == offsets.end()) {
+          if ((int)offsets.size() == kDiaMax) return false;
+          offsets.push_back(off);
+        }
+      }
+      return true;
+    };
+    const int64_t stride = std::max<int64_t>(1, n / 4096);
+    for (int64_t i = 0; i < n; i += stride)
+      if (!scan_row(i)) return LLZ_OK;
+    for (int64_t i = 0; i < std::min<int64_t>(n, 64); ++i)
+      if (!scan_row(i) || !scan_row(n - 1 - i)) return LLZ_OK;
+    if (offsets.empty()) return LLZ_OK;
+    const int nd = (int)offsets.size();
+    if ((double)nd * (double)n > 1.3 * (double)nnz) return LLZ_OK;  // too many absent entries: SELL stores less
+    std::sort(offsets.begin(), offsets.end());
+    if (offsets.front() < -(n + (int64_t)halo_lo) || offsets.back() > n + n_hi) return LLZ_OK;
+    DiaOffsets offs;
+    offs.nd = nd;
+    for (int d = 0; d < nd; ++d) offs.off[d] = (int)offsets[(size_t)d];
+    const int64_t ldv = (n + 31) / 32 * 32;
+    T* dv = nullptr;
+    uint16_t* dm = nullptr;
+    cudaError_t e = dev_malloc(ctx, &dv, sizeof(T) * (size_t)ldv * nd);
+    if (e == cudaSuccess) e = dev_malloc(ctx, &dm, sizeof(uint16_t) * (size_t)n);
+    if (e != cudaSuccess) {  // not enough room for both copies: keep what we have
+      if (dv) dev_free(ctx, dv);
+      (void)cudaGetLastError();
+      return LLZ_OK;
+    }
+    int* d_bad = reinterpret_cast<int*>(ctx->d_result);
+    e = cudaMemsetAsync(dv, 0, sizeof(T) * (size_t)ldv * nd, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+    if (e == cudaSuccess) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 8));
+      k_dia_fill<T, IDX><<<grid, kThreads, 0, ctx->stream>>>((const IDX*)d_rowptr, d_colidx, d_vals, n, halo_lo, offs, ldv, dv, dm, d_bad);
+      e = cudaGetLastError();
+      ctx->launches++;
+    }
+    int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || bad) {
+      dev_free(ctx, dv);
+      dev_free(ctx, dm);
+      if (e != cudaSuccess) return fail(LLZ_ERR_CUDA, "DIA conversion: %s", cudaGetErrorString(e));
+      return LLZ_OK;
+    }
+    d_dvals = dv;
+    d_dmask = dm;
+    dia_offs = offs;
+    dia_ld = ldv;
+    dev_free(ctx, d_rowptr);
+    dev_free(ctx, d_colidx);
+    dev_free(ctx, d_vals);
+    d_rowptr = nullptr;
+    d_colidx = nullptr;
+    d_vals = nullptr;
+    dia = true;
+    bytes = (int64_t)nd * n * (int64_t)sizeof(T) + 2 * n;
+    *done = true;
+    return LLZ_OK;
+  }
+
   // Re-store the uploaded CSR arrays as SELL-32-sigma, entirely on the device (only the slice widths visit the host
   // for the prefix sum).  sigma: 1 = keep the row order, 32..1024 (multiple of 32) = sort windows of sigma rows by
   // length, 0 = pick (sort only if it saves more than 5 % of the padded storage).
@@ -738,7 +951,9 @@ template <class T> struct CsrOp : OpBase {
   int abs_row_sum_max(double* out) override {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_local + kThreads - 1) / kThreads, (int64_t)ctx->num_sms * 4));
     double* d = ctx->d_partials;  // kMaxGrid * 2 doubles
-    if (sell)
+    if (dia)
+      k_dia_rowsum_max<T><<<grid, kThreads, 0, ctx->stream>>>(d_dvals, dia_ld, dia_offs.nd, n_local, d);
+    else if (sell)
       k_sell_rowsum_max<T><<<grid, kThreads, 0, ctx->stream>>>(d_slice_ptr, d_sval, n_slices, d);
     else if (idx32)
       k_csr_rowsum_max<T, int32_t><<<grid, kThreads, 0, ctx->stream>>>((const int32_t*)d_rowptr, d_vals, n_local, d);
@@ -754,6 +969,7 @@ template <class T> struct CsrOp : OpBase {
 
   int apply_fused(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg* alpha_msg) override {
     const PeerMsg msg = alpha_msg ? *alpha_msg : PeerMsg();
+    if (dia) return launch_dia(x, y, sigma, pa, npa, msg);
     if (sell) return launch_sell(x, y, sigma, pa, npa, msg);
     if (stream_rows > 0) return idx32 ? launch_stream<int32_t>(x, y, sigma, pa, npa, msg) : launch_stream<int64_t>(x, y, sigma, pa, npa, msg);
     return idx32 ? launch_lpr<int32_t>(x, y, sigma, pa, npa, msg) : launch_lpr<int64_t>(x, y, sigma, pa, npa, msg);
@@ -785,6 +1001,15 @@ static int plan_sharded_csr(CsrOp<T>* op, int64_t row0, const int64_t* rowptr, c
   std::vector<int32_t> halo_cols;
   LLZ_TRY(halo_plan_vectors(n_rows, row0, rowptr, colidx, G, bounds.data(), col_local.data(), halo_cols, need.data()));
   const int64_t n_halo = (int64_t)halo_cols.size();
+  {  // is the halo exactly the rows just below and just above the block?  (what the DIA storage can address)
+    int64_t lo = 0;
+    while (lo < n_halo && halo_cols[(size_t)lo] < row0) ++lo;
+    bool contig = true;
+    for (int64_t t = 0; t < lo && contig; ++t) contig = halo_cols[(size_t)t] == row0 - lo + t;
+    for (int64_t t = lo; t < n_halo && contig; ++t) contig = halo_cols[(size_t)t] == row0 + n_rows + (t - lo);
+    op->halo_lo = (int32_t)lo;
+    op->halo_contiguous = contig;
+  }
   // need_all[q*G + p] = number of entries rank q needs from rank p
   std::vector<int64_t> need_all((size_t)G * G);
   LLZ_TRY(comm_allgather_host(ctx, need.data(), need_all.data(), sizeof(int64_t) * G));
@@ -986,7 +1211,19 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
   while (lpr < 32 && lpr < mean) lpr *= 2;
   op->lpr = lpr;
   op->bytes = last * (int64_t)(sizeof(T) + 4) + (n_rows + 1) * (op->idx32 ? 4 : 8);
-  if (sell_sigma >= 0) {
+  bool as_dia = false;
+  {
+    const char* env = getenv("LLZ_DIA");
+    const int32_t* host_cols = ctx->nranks > 1 ? col_local.data() : (host_arrays ? colidx_in : nullptr);
+    if (sell_sigma == 0 && host_cols && !(env && env[0] == '0')) {
+      s = op->idx32 ? op->template convert_to_dia<int32_t>(rowptr, host_cols, &as_dia) : op->template convert_to_dia<int64_t>(rowptr, host_cols, &as_dia);
+      if (s != LLZ_OK) {
+        delete op;
+        return s;
+      }
+    }
+  }
+  if (sell_sigma >= 0 && !as_dia) {
     s = op->idx32 ? op->template convert_to_sell<int32_t>(sell_sigma) : op->template convert_to_sell<int64_t>(sell_sigma);
     if (s != LLZ_OK) {
       delete op;
@@ -1003,6 +1240,7 @@ static int create_csr(llz_ctx_t ctx, int dtype, int64_t n_rows, int64_t n_cols, 
 // User callback adapter
 // ------------------------------------------------------------------------------------------------------------------
 struct CallbackOp : OpBase {
+  const char* storage() const override { return "user callback"; }
   llz_apply_fn fn = nullptr;
   void* user = nullptr;
   bool overwrites = false;
@@ -1125,6 +1363,8 @@ int llz_op_gerschgorin_radius(llz_op_t op, double* radius) {
   *radius = *std::max_element(all.begin(), all.end());
   return LLZ_OK;
 }
+
+const char* llz_op_storage(llz_op_t op) { return (op && op->impl) ? op->impl->storage() : ""; }
 
 int llz_op_bytes(llz_op_t op, int64_t* bytes) {
   if (!op || !bytes) return fail(LLZ_ERR_INVALID, "null");

@@ -586,6 +586,7 @@ struct XxzOpBase : OpBase {
     if (xb) comm_exchange_buffer_release(ctx, xb);
   }
   virtual int plan_block_kernel() = 0;
+  const char* storage() const override { return per_state ? "XXZ matrix-free (state table)" : "XXZ matrix-free (block kernel)"; }
   size_t vec_bytes() const { return ((size_t)n_global * dtype_size(dtype) + 255) / 256 * 256; }  // stride between the two copies
   bool plan_push(GatherPush* push) override {
     if (!xb) return false;

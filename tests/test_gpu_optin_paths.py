@@ -8,6 +8,8 @@ Each switch is read when the library, the context or an operator is created, so 
   LLZ_BASIS_VMM=0    one cudaMalloc for the Krylov basis instead of the VMM store    -> everything bit-identical
   LLZ_FUSED_ORTH=0   project / reduce / update / scale as separate launches          -> runs to rounding, same counts
   LLZ_XXZ_KERNEL=state  one-thread-per-state XXZ kernel instead of the block kernel  -> y bit-identical
+  LLZ_DIA=0          SELL instead of DIA storage for stencil operators               -> y bit-identical
+  (LLZ_DIA=0 + LLZ_SELL_TMA=1: the TMA kernel on the stencil operators the default run stores as DIA)
 """
 import json
 import os
@@ -19,7 +21,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SWITCHES = ("LLZ_SELL_TMA", "LLZ_SPMV", "LLZ_BASIS_VMM", "LLZ_FUSED_ORTH", "LLZ_XXZ_KERNEL", "LLZ_XXZ_M")
+SWITCHES = ("LLZ_SELL_TMA", "LLZ_SPMV", "LLZ_BASIS_VMM", "LLZ_FUSED_ORTH", "LLZ_XXZ_KERNEL", "LLZ_XXZ_M", "LLZ_DIA")
 
 
 def run_worker(extra):
@@ -48,12 +50,13 @@ def close_runs(a, b, same_vectors):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("switch,value,bitwise", [("LLZ_SELL_TMA", "1", False), ("LLZ_SPMV", "v", False), ("LLZ_BASIS_VMM", "0", True),
-                                                  ("LLZ_FUSED_ORTH", "0", False), ("LLZ_XXZ_KERNEL", "state", False)])
+                                                  ("LLZ_FUSED_ORTH", "0", False), ("LLZ_XXZ_KERNEL", "state", False), ("LLZ_DIA", "0", False),
+                                                  ("LLZ_DIA+TMA", "0", False)])
 def test_opt_in_path_matches_default(default_result, switch, value, bitwise):
     """`bitwise`: whole runs reproduce bit for bit (the switch changes no floating-point operation order at all).  The
     applies (y = A x) are compared bit for bit for every switch but LLZ_SPMV=v; a different alpha-dot reduction tree
     (XXZ kernels) or register tile (fused orthogonalisation at small n) moves a run by rounding only."""
-    got = run_worker({switch: value})
+    got = run_worker({"LLZ_DIA": "0", "LLZ_SELL_TMA": "1"} if switch == "LLZ_DIA+TMA" else {switch: value})
     assert got.keys() == default_result.keys()
     for key, ref in default_result.items():
         val = got[key]

@@ -238,6 +238,46 @@ def test_xxz_block_kernel_is_bit_identical_to_per_state_kernel(pkg, ctx, wl, mon
         assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), (m, np.abs(y - y_ref).max())
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+def test_dia_storage_is_picked_for_stencils_and_is_bit_identical_to_csr(pkg, ctx, wl, dtype):
+    """llz_op_create_sell(sigma = 0) re-stores operators whose non-zeros lie on <= 16 diagonals diagonal by diagonal (no
+    column indices, contiguous shifted x reads); y must equal the CSR kernels' bit for bit (same products, same order),
+    absent entries (grid boundaries) are skipped, and anything else falls back to SELL."""
+    import scipy.sparse as sp
+
+    cases = {"laplacian 37x41": wl.laplacian2d_csr(37, 41, dtype=dtype), "chain": wl.dense_to_csr(np.diag(np.ones(9), 1) + np.diag(np.ones(9), -1)),
+             "laplacian 64x64": wl.laplacian2d_csr(64, dtype=dtype)}
+    if np.dtype(dtype).kind == "c":
+        full = wl.peierls_csr(33, 29, flux=0.07, trap=0.1)
+        cases["peierls 33x29"] = (full[0], full[1], full[2].astype(dtype))
+    for name, csr in cases.items():
+        csr = (csr[0], csr[1], csr[2].astype(dtype))
+        n = csr[0].size - 1
+        op = pkg.Operator.sell(ctx, *csr)
+        assert op.storage() == "DIA", (name, op.storage())
+        x = rnd(np.random.RandomState(3), n, dtype)
+        y_csr = pkg.Operator.csr(ctx, *csr).matvec(x)
+        assert np.array_equal(op.matvec(x).view(np.uint8), y_csr.view(np.uint8)), name
+        assert op.bytes() < pkg.Operator.sell(ctx, *csr, sigma=1).bytes()
+        xi = x.copy()
+        xi[n // 2] = np.inf  # an Inf in x reaches exactly the rows that reference it
+        assert np.array_equal(np.isfinite(op.matvec(xi)), np.isfinite(pkg.Operator.csr(ctx, *csr).matvec(xi))), name
+        assert abs(op.gerschgorin_radius() - pkg.Operator.csr(ctx, *csr).gerschgorin_radius()) < 1e-5
+    # 17 diagonals, or non-zeros off the sampled diagonals: SELL
+    n = 500
+    many = sp.diags([np.ones(n - abs(k)) for k in range(-8, 9)], list(range(-8, 9)), format="csr")
+    csr = (many.indptr.astype(np.int64), many.indices.astype(np.int32), many.data.astype(dtype))
+    assert pkg.Operator.sell(ctx, *csr).storage().startswith("SELL")
+    stray = sp.lil_matrix(sp.diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1], format="csr").astype(np.float64))
+    stray[301, 17] = stray[17, 301] = 0.5  # rows the sample of candidate diagonals does not visit... or visits: SELL either way
+    stray = sp.csr_matrix(stray)
+    stray.sort_indices()
+    csr = (stray.indptr.astype(np.int64), stray.indices.astype(np.int32), stray.data.astype(dtype))
+    op = pkg.Operator.sell(ctx, *csr)
+    x = rnd(np.random.RandomState(4), n, dtype)
+    assert np.array_equal(op.matvec(x).view(np.uint8), pkg.Operator.csr(ctx, *csr).matvec(x).view(np.uint8))
+
+
 # ---- the Lanczos recurrence itself: alpha, beta and the basis, iteration by iteration -------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_lanczos_vectors_match_oracle_iteration_by_iteration(pkg, ctx, wl, oracle_mod, port, dtype):

@@ -18,19 +18,20 @@ def run(name, op, dtype):
     ctx.synchronize(); ms, cnt, by = ctx.profile_read("spmv"); ctx.profile(False)
     itemsize = np.dtype(dtype).itemsize
     alg = op.bytes() + 2 * n * itemsize
-    print(f"{name:28s} n={n:10d} {ms/cnt*1e3:9.1f} us/apply  A_bytes={op.bytes()/1e6:9.1f} MB  algorithmic {alg/(ms/cnt*1e-3)/1e9:7.0f} GB/s"
+    print(f"{name:28s} [{op.storage():22s}] n={n:10d} {ms/cnt*1e3:9.1f} us/apply  A_bytes={op.bytes()/1e6:9.1f} MB  algorithmic {alg/(ms/cnt*1e-3)/1e9:7.0f} GB/s"
           f"  (x,y-only {2*n*itemsize/(ms/cnt*1e-3)/1e9:6.0f} GB/s)", flush=True)
 
 for w in which:
     if w == "laplacian":
         csr = wl.laplacian2d_csr(4096)
         run("laplacian4096 csr", pkg.Operator.csr(ctx, *csr), np.float64)
-        run("laplacian4096 sell", pkg.Operator.sell(ctx, *csr), np.float64)
-        run("laplacian4096 sell sigma=256", pkg.Operator.sell(ctx, *csr, sigma=256), np.float64)
+        run("laplacian4096 auto", pkg.Operator.sell(ctx, *csr), np.float64)
+        run("laplacian4096 sell sigma=1", pkg.Operator.sell(ctx, *csr, sigma=1), np.float64)
     elif w == "peierls":
         csr = wl.peierls_csr(2896, 2896)
         run("peierls2896 csr c128", pkg.Operator.csr(ctx, *csr), np.complex128)
-        run("peierls2896 sell c128", pkg.Operator.sell(ctx, *csr), np.complex128)
+        run("peierls2896 auto c128", pkg.Operator.sell(ctx, *csr), np.complex128)
+        run("peierls2896 sell sigma=1 c128", pkg.Operator.sell(ctx, *csr, sigma=1), np.complex128)
     elif w == "random":
         csr = wl.random_symmetric_csr(100000)
         run("random100k csr", pkg.Operator.csr(ctx, *csr), np.float64)
