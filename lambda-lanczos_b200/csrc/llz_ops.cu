@@ -475,38 +475,57 @@ __global__ void __launch_bounds__(kThreads) k_dia_fill(const IDX* __restrict__ r
 }
 
 template <class T, int ND, bool SHARDED>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, ND <= 3 ? 4 : (ND <= 6 ? 3 : 2))
     k_dia_spmv_dot(const T* __restrict__ dvals, int64_t ldv, const uint16_t* __restrict__ mask, DiaOffsets offs, const T* __restrict__ x,
                    const T* halo, int32_t n_lo, T* __restrict__ y, int64_t n, typename Num<T>::R sigma, double* pa, PeerMsg msg,
                    PeerMsg halo_msg) {
   __shared__ double scratch[kWarps];
   if (SHARDED && halo_msg.ch.G > 0) peer_wait(halo_msg.ch, halo_msg.seq);
+  constexpr int U = (sizeof(T) <= 8 && ND <= 8) ? 2 : 1;  // rows per thread and step (loads in flight vs registers)
   double dot = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    const uint32_t m = mask[i];
-    T a[ND], xv[ND];
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += stride * U) {
+    uint32_t m[U];
+    T a[U][ND], xv[U][ND], xi[U];
+    // every load of the step is issued before the first is used; the presence mask only gates the arithmetic (absent
+    // entries are stored as zeros, and the x index of an absent entry is clamped into the vector), so nothing waits
+    // for the mask
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      const bool on = d < offs.nd && ((m >> d) & 1u);
-      a[d] = on ? __ldg(dvals + (int64_t)d * ldv + i) : zero_of(T());
-      if (on) {
-        const int64_t e = i + offs.off[d];
-        if (!SHARDED || (e >= 0 && e < n))
-          xv[d] = __ldg(x + e);
-        else
-          xv[d] = __ldcg(halo + (e < 0 ? n_lo + e : n_lo + (e - n)));  // written by the peers: coherent load
-      } else {
-        xv[d] = zero_of(T());
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool row = i < n;
+      const int64_t ic = row ? i : n - 1;
+      m[u] = row ? mask[ic] : 0u;
+      xi[u] = x[ic];
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        if (d < offs.nd) {
+          a[u][d] = __ldg(dvals + (int64_t)d * ldv + ic);
+          const int64_t e = ic + offs.off[d];
+          if (e >= 0 && e < n) {
+            xv[u][d] = __ldg(x + e);
+          } else if (SHARDED) {
+            const int64_t h = e < 0 ? n_lo + e : n_lo + (e - n);
+            xv[u][d] = ((m[u] >> d) & 1u) ? __ldcg(halo + h) : zero_of(T());  // written by the peers: coherent load
+          } else {
+            xv[u][d] = zero_of(T());
+          }
+        }
       }
     }
-    T sum = zero_of(T());
 #pragma unroll
-    for (int d = 0; d < ND; ++d)
-      if (d < offs.nd && ((m >> d) & 1u)) sum = add_rn(sum, mul_rn(a[d], xv[d]));
-    const T xi = x[i];
-    const T yi = add_t(sum, scale_real(xi, sigma));
-    y[i] = yi;
-    dot += re_conj_mul(xi, yi);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        T sum = zero_of(T());
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          if (d < offs.nd && ((m[u] >> d) & 1u)) sum = add_rn(sum, mul_rn(a[u][d], xv[u][d]));
+        const T yi = add_t(sum, scale_real(xi[u], sigma));
+        y[i] = yi;
+        dot += re_conj_mul(xi[u], yi);
+      }
+    }
   }
   const double t = block_sum(dot, scratch);
   finish_scalar(t, pa, msg, scratch);
@@ -766,7 +785,10 @@ template <class T> struct CsrOp : OpBase {
     return LLZ_OK;
   }
   int launch_dia(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {
-    return dia_offs.nd <= 8 ? launch_dia_nd<8>(x, y, sigma, pa, npa, msg) : launch_dia_nd<16>(x, y, sigma, pa, npa, msg);
+    if (dia_offs.nd <= 3) return launch_dia_nd<3>(x, y, sigma, pa, npa, msg);   // 1-D chains
+    if (dia_offs.nd <= 6) return launch_dia_nd<6>(x, y, sigma, pa, npa, msg);   // 2-D 5-point stencils, square-lattice hopping
+    if (dia_offs.nd <= 8) return launch_dia_nd<8>(x, y, sigma, pa, npa, msg);   // 3-D 7-point stencils
+    return launch_dia_nd<16>(x, y, sigma, pa, npa, msg);
   }
 
   // Re-store the uploaded CSR arrays diagonal by diagonal when (almost) every non-zero sits on one of at most 16
