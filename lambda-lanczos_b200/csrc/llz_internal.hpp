@@ -44,6 +44,7 @@ struct Comm;         // inter-GPU plumbing (llz_comm.cu)
 struct PeerChannel;  // peer-memory message channel (llz_peer.cuh)
 struct PeerMsg;
 struct GatherPush;
+struct HaloPushPlan;
 
 // Per-kernel device-time accounting (CUDA events on the context's stream), keyed by a short kernel-family name.
 struct ProfEntry {
@@ -133,6 +134,15 @@ struct OpBase {
     (void)push;
     (void)scale;
   }
+  // Halo of a row-sharded sparse operator: the kernel that produces (and normalises) the next input vector stores the
+  // entries the peers reference into their halo segments itself.  plan_halo_push() hands it the plan (false: not
+  // supported / nothing to send — prepare() does the exchange before the apply as usual); use_pushed_halo() tells the
+  // operator that its next apply finds the halo announced by that plan's message.
+  virtual bool plan_halo_push(HaloPushPlan* plan) {
+    (void)plan;
+    return false;
+  }
+  virtual void use_pushed_halo(const HaloPushPlan& plan) { (void)plan; }
   // max_i sum_j |a_ij| over the LOCAL rows (Gerschgorin radius); LLZ_ERR_UNSUPPORTED for operators without stored
   // or analytically known entries (user callbacks).
   virtual int abs_row_sum_max(double* out) {

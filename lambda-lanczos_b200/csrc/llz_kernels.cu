@@ -498,6 +498,7 @@ struct OrthArgs {
   int nred;  // CTAs that take part in the reduction (32 values each)
   UpdateArgs u;
   ScaleNormArgs s;
+  HaloPushPlan halo;            // row-sharded sparse operators: push the normalised vector's halo entries to the peers
   unsigned long long* bar;      // device counter, monotonic across launches
   unsigned long long bar_base;  // its value when this launch starts
 };
@@ -533,13 +534,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_orth(OrthArgs a) {
   update_body<T, VPT, CT>(a.u, smem_o);  // (row-sharded: waits for the peers' coefficient messages in its prologue)
   grid_barrier(a, 3);
   const double beta = norm_and_publish(a.s, scratch);
-  if (!(beta > 0.0) || !isfinite(beta)) return;
-  const R inv = (R)1 / (R)beta;
+  const bool scale = beta > 0.0 && isfinite(beta);  // breakdown: the reference leaves u_k un-normalised (:279-283)
+  const R inv = scale ? (R)1 / (R)beta : (R)1;
   // every thread re-scales exactly the packets it wrote in the update phase (same slab walk)
   T* x = reinterpret_cast<T*>(a.u.out);
   constexpr int64_t SLAB = (int64_t)kThreads * VPT * VEC;
   const int64_t nslabs = (a.u.n + SLAB - 1) / SLAB;
-  for (int64_t sl = blockIdx.x; sl < nslabs; sl += gridDim.x) {
+  for (int64_t sl = blockIdx.x; scale && sl < nslabs; sl += gridDim.x) {
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
       const int64_t idx = sl * SLAB + (int64_t)(i * kThreads + threadIdx.x) * VEC;
@@ -554,6 +555,28 @@ __global__ void __launch_bounds__(kThreads, 2) k_orth(OrthArgs a) {
           if (idx + e < a.u.n) x[idx + e] = scale_real(x[idx + e], inv);
       }
     }
+  }
+  if (a.halo.hp.G == 0) return;
+  // ---- halo of the next operator application: the normalised entries the peers reference, straight into their halo
+  //      segments over NVLink (what k_halo_push would do in a launch of its own before the apply) ----
+  grid_barrier(a, 4);  // every packet of the vector is final (and visible: the loads below go to L2)
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.halo.n_send; i += (long long)gridDim.x * kThreads) {
+    int q = 0;
+    while (i >= a.halo.hp.start[q + 1]) ++q;
+    reinterpret_cast<T*>(a.halo.hp.dst[q])[i - a.halo.hp.start[q]] = __ldcg(x + a.halo.idx[i]);
+  }
+  __shared__ int last_cta;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative: covers the stores of the whole CTA ordered before it by the barrier
+    const unsigned int t = atomicAdd(a.halo.msg.ticket, 1u);
+    last_cta = (t == gridDim.x - 1);
+    if (last_cta) *a.halo.msg.ticket = 0;
+  }
+  __syncthreads();
+  if (last_cta && (int)threadIdx.x < a.halo.msg.ch.G) {
+    __threadfence_system();
+    peer_announce(a.halo.msg.ch, threadIdx.x, a.halo.msg.seq);
   }
 }
 
@@ -1069,7 +1092,7 @@ static int orth_impl(llz_ctx_t ctx, OrthArgs& a, int* fused, int* grid_out) {
   a.s.npb = grid;
   a.bar = ctx->d_bar;
   a.bar_base = ctx->bar_count;
-  ctx->bar_count += 3ull * (unsigned long long)grid;
+  ctx->bar_count += (a.halo.hp.G > 0 ? 4ull : 3ull) * (unsigned long long)grid;
   void* params[] = {&a};
   cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_orth<T, VPT, CT>, dim3((unsigned)grid), dim3(kThreads), params, smem, ctx->stream);
   if (le != cudaSuccess) return fail(LLZ_ERR_CUDA, "launch k_orth: %s", cudaGetErrorString(le));
@@ -1094,8 +1117,8 @@ bool orth_fusable(llz_ctx_t ctx, int dtype, int total_cols, int64_t n) {
 }
 
 int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t n, const Fold& fold, double* ph, double* coef,
-                double* wnorm2, const PeerMsg& coef_msg, int wnorm_index, double* norm_partials, const ScalarSink& sink, int* fused,
-                int* grid_out) {
+                double* wnorm2, const PeerMsg& coef_msg, int wnorm_index, double* norm_partials, const ScalarSink& sink,
+                const HaloPushPlan& halo, int* fused, int* grid_out) {
   *fused = 0;
   const int total = cs.ncols();
   if (total < 1 || total > max_project_cols(dtype)) return LLZ_OK;
@@ -1108,6 +1131,7 @@ int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t 
   a.s.pb = norm_partials;
   a.s.npb = 0;
   a.s.sink = sink;
+  a.halo = halo;
   LLZ_DISPATCH(dtype, {
     if (pick_vpt<T>(ctx, n) == 2) return orth_impl<T, 2, kCT>(ctx, a, fused, grid_out);
     return orth_impl<T, 1, small_ct<T>()>(ctx, a, fused, grid_out);

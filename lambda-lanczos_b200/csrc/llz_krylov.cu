@@ -98,6 +98,8 @@ struct llz_krylov_s {
   int64_t pushed_col = -1;
   OpBase* pushed_op = nullptr;
   GatherPush pushed;
+  bool halo_pushed = false;  // ... or, for sparse operators, its halo entries into the peers' halo segments
+  HaloPushPlan halo_plan;
   // state
   int64_t k = 0;
 
@@ -244,6 +246,7 @@ int llz_krylov_create(llz_ctx_t ctx, int dtype, int64_t n, int64_t max_cols, llz
       c->k = 0;
       c->nq = 0;
       c->pushed_valid = false;
+      c->halo_pushed = false;
       c->h_flag[0] = 0;
       *out = c;
       return LLZ_OK;
@@ -432,6 +435,7 @@ int llz_krylov_begin(llz_krylov_t kry, const void* start, int host, double* norm
   }
   kry->k = 0;
   kry->pushed_valid = false;
+  kry->halo_pushed = false;
   kry->h_flag[0] = 0;
   const size_t bytes = (size_t)kry->n * dtype_size(kry->dtype);
   void* u0 = kry->col(0);
@@ -479,10 +483,13 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     // the previous iteration's update / recurrence kernel already delivered x to every GPU (un-normalised: the
     // consumer divides the remote entries by beta_{k-2}, as k_scale_norm did with the local block)
     op->impl->use_pushed(kry->pushed, kry->d_beta + (k - 2));
+  } else if (kry->halo_pushed && kry->pushed_op == op->impl && kry->pushed_col == k - 1) {
+    op->impl->use_pushed_halo(kry->halo_plan);  // the fused kernel of the previous iteration pushed the halo of x
   } else {
     LLZ_TRY(op->impl->prepare(x));
   }
   kry->pushed_valid = false;
+  kry->halo_pushed = false;
   Fold fold;
   fold.alpha_msg = comm_next_message(ctx, kChanAlpha);  // delivered by the last CTA of the kernel that computes <x, Ax>
   {
@@ -545,9 +552,16 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
       sink.flag_value = k;
       const double es = (double)dtype_size(kry->dtype);
       ProfScope ps(ctx, "orth", (double)kry->n * es * ((total + 1 + fold.mode) + (total + 2) + 2));
+      HaloPushPlan halo;
+      if (peer && !kry->pushed_valid && op->impl->plan_halo_push(&halo)) {  // ... and the halo of u_k for the next apply
+        kry->halo_pushed = true;
+        kry->pushed_col = k;
+        kry->pushed_op = op->impl;
+        kry->halo_plan = halo;
+      }
       int fused = 0;
       LLZ_TRY(launch_orth(ctx, kry->dtype, cs, y, kry->n, fold, kry->d_ph, kry->d_coef, kry->d_misc + 1, coef_msg, peer ? total * nc : -1,
-                          kry->d_pb, sink, &fused, &grid));
+                          kry->d_pb, sink, halo, &fused, &grid));
       if (!fused) return fail(LLZ_ERR_CUDA, "krylov_step: the fused orthogonalisation kernel declined a shape it had accepted");
       kry->k = k;
       return LLZ_OK;
@@ -631,6 +645,7 @@ int llz_krylov_refine(llz_krylov_t kry, int64_t k, double* shrink) {
   LLZ_CUDA(cudaStreamSynchronize(ctx->stream));
   kry->k = k;  // iterations enqueued beyond k used the un-refined vector: drop them
   kry->pushed_valid = false;  // ... and so did the copy of it the peers were sent
+  kry->halo_pushed = false;
   kry->h_flag[0] = k;
   if (shrink) *shrink = nu;
   return LLZ_OK;

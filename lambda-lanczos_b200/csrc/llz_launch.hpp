@@ -89,8 +89,8 @@ int launch_update(llz_ctx_t ctx, int dtype, const ColumnSet& cs, int col0, int n
 // *fused = 0 and nothing is launched when the shape does not allow it; the caller then issues the separate kernels.
 bool orth_fusable(llz_ctx_t ctx, int dtype, int total_cols, int64_t n);  // ask BEFORE drawing peer messages for the step
 int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t n, const Fold& fold, double* ph, double* coef,
-                double* wnorm2, const PeerMsg& coef_msg, int wnorm_index, double* norm_partials, const ScalarSink& sink, int* fused,
-                int* grid_out);
+                double* wnorm2, const PeerMsg& coef_msg, int wnorm_index, double* norm_partials, const ScalarSink& sink,
+                const HaloPushPlan& halo, int* fused, int* grid_out);
 // x *= 1/sqrt(sum partials); publishes beta (and alpha) per `sink`.  Leaves x untouched when the norm is not > 0.
 int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
                          const ScalarSink& sink);

@@ -50,12 +50,6 @@ template <class T> __global__ void __launch_bounds__(kThreads) k_pack(const T* _
 // Peer-memory halo exchange: instead of pack -> ncclSend/ncclRecv, every rank stores the entries its peers need straight
 // into their halo buffers (sub-allocations of the IPC-mapped window, double-buffered by message parity) and the last
 // CTA announces the message; the SpMV kernels wait for the G announcements in their prologue.
-struct HaloPush {
-  int G = 0;
-  long long start[kMaxRanks + 1] = {};  // send entries [start[q], start[q+1]) go to rank q
-  void* dst[kMaxRanks] = {};            // where they go (address of rank q's halo segment for this rank, mapped here)
-};
-
 template <class T>
 __global__ void __launch_bounds__(kThreads) k_halo_push(const T* __restrict__ x, const int32_t* __restrict__ idx, long long n_send, HaloPush hp, PeerMsg msg) {
   __shared__ int last_cta;
@@ -682,6 +676,22 @@ template <class T> struct CsrOp : OpBase {
     }
     return comm_exchange(ctx, (const char*)d_sendbuf, send_off.data(), send_bytes.data(), (char*)d_halo, recv_off.data(),
                          recv_bytes.data());
+  }
+
+  bool plan_halo_push(HaloPushPlan* plan) override {
+    if (ctx->nranks == 1 || win_off < 0) return false;
+    plan->msg = comm_next_message(ctx, kChanHalo);
+    plan->hp = push;
+    if (plan->msg.seq & 1ull)
+      for (int q = 0; q < plan->hp.G; ++q) plan->hp.dst[q] = static_cast<char*>(plan->hp.dst[q]) + push_stride[q];
+    plan->idx = d_send_idx;
+    plan->n_send = n_send;
+    return true;
+  }
+  void use_pushed_halo(const HaloPushPlan& plan) override {
+    cur_halo = reinterpret_cast<const T*>(static_cast<char*>(comm_window_ptr(ctx, ctx->rank, win_off)) +
+                                          ((plan.msg.seq & 1ull) ? (size_t)std::max<int64_t>(n_halo, 1) * sizeof(T) : 0));
+    cur_halo_msg = plan.msg;
   }
 
   template <class IDX, int LPR> int launch(const void* x, void* y, double sigma, double* pa, int* npa, const PeerMsg& msg) {

@@ -51,6 +51,21 @@ struct GatherPush {
   PeerMsg msg;
 };
 
+// Halo of a row-sharded CSR / SELL / DIA operator pushed by the owner: entries idx[start[q] .. start[q+1]) of the local
+// vector go to dst[q], rank q's halo segment for this rank (mapped here).  Either a kernel of its own before the apply
+// (k_halo_push) or the tail of the fused orthogonalisation kernel, which has just produced the vector.
+struct HaloPush {
+  int G = 0;
+  long long start[kMaxRanks + 1] = {};  // send entries [start[q], start[q+1]) go to rank q
+  void* dst[kMaxRanks] = {};            // where they go
+};
+struct HaloPushPlan {
+  HaloPush hp;                  // hp.G == 0: nothing to push
+  const int32_t* idx = nullptr; // [n_send] local indices, grouped by requesting rank
+  long long n_send = 0;
+  PeerMsg msg;                  // announced by the last CTA once every entry is stored
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ double* peer_slot(const PeerChannel& ch, int owner, unsigned long long seq, int src) {
   return ch.inbox[owner] + ((size_t)(seq & 1ull) * ch.G + src) * ch.payload;

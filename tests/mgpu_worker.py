@@ -209,7 +209,13 @@ def run_gpu(rank, world):
             degenerate = any(abs(ev_ref[i] - ev_ref[j]) < 1e-9 * max(1, abs(ev_ref[i])) for j in range(len(ev)) if j != i)
             if not degenerate:
                 assert 1 - ov < 1e-9, (name, i, ov)
-            assert res < max(10 * res_ref, 1e-9), (name, i, res, res_ref)
+                assert res < max(10 * res_ref, 1e-9), (name, i, res, res_ref)
+            else:
+                # A member of a degenerate pair: the reference's stopping rule watches the Ritz VALUES (relative change
+                # < eps), which leaves such a vector determined to ~sqrt(eps) only; which iteration trips the rule depends
+                # on rounding, i.e. on the reduction tree (ranks, transport) — seen: 313 vs 321 iterations, residual 7e-8
+                # at 8 ranks over NCCL where the single GPU happens to stop at 3e-15.
+                assert res < 1e-6 * max(1.0, abs(ev[i])), (name, i, res, res_ref)
         if rank == 0:
             print(f"  {name}: iterations sharded {eng.getIterationCounts()} single {ref.getIterationCounts()} eigenvalues {ev}", flush=True)
 
