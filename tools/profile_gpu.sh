@@ -17,6 +17,7 @@ for K in 20 100 180; do
   # first Lanczos run of the timed step: launch index = warm-up step (~1600) + 3 (begin) + 2 K
   timeout 900 $NCU --set full --import-source on -k 'regex:k_orth|k_dia_spmv_dot|k_sell_spmv_dot' -s $((800 + K)) -c 2 -f -o $OUT/iteration_${TAG}_k$K $BENCH > $OUT/iteration_${TAG}_k$K.log 2>&1
   ncu -i $OUT/iteration_${TAG}_k$K.ncu-rep --page raw --csv > $OUT/iteration_${TAG}_k${K}_raw.csv 2>/dev/null
+  ncu -i $OUT/iteration_${TAG}_k$K.ncu-rep --page details > $OUT/iteration_${TAG}_k${K}_details.txt 2>/dev/null
 done
 for DT in f64; do
   timeout 300 $NCU --set full --import-source on -k regex:k_xxz_block_apply -s 3 -c 1 -f -o $OUT/xxz28_${TAG} python tools/bench_xxz.py 28 block > $OUT/xxz28_${TAG}.log 2>&1
@@ -27,4 +28,5 @@ timeout 300 $NCU --set full -k regex:k_xxz_block_apply -s 26 -c 1 -f -o $OUT/xxz
 ncu -i $OUT/xxz28c_${TAG}.ncu-rep --page raw --csv > $OUT/xxz28c_${TAG}_raw.csv 2>/dev/null
 timeout 300 $NCU --set full -k regex:k_dia_spmv_dot -s 3 -c 1 -f -o $OUT/dia_${TAG} python tools/bench_spmv.py laplacian > $OUT/dia_${TAG}.log 2>&1
 ncu -i $OUT/dia_${TAG}.ncu-rep --page raw --csv > $OUT/dia_${TAG}_raw.csv 2>/dev/null
+rm -f $OUT/*_${TAG}*.ncu-rep  # the exported csv / details pages are what travels back (gpurun_out is capped at 64 MiB)
 ls -la $OUT | tail -12
