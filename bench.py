@@ -44,12 +44,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-# DRAM traffic / algorithmic bytes of the two basis-streaming kernels, from the committed `ncu --set full` captures
+# DRAM traffic / algorithmic bytes of the basis-streaming kernels, from the committed `ncu --set full` captures
 # (dram__bytes_read.sum + dram__bytes_write.sum per launch over the algorithmic bytes of that very launch):
-# profiles/r01b_ncu_full_summary.txt (k = 151, n = 16.7 M): project 20.68 / 20.67 GB, update 20.36 / 20.53 GB;
-# profiles/r02_ncu_traffic_by_k.txt holds the same ratio at other k and at the per-GPU shape of an 8-GPU run.
-NCU_TRAFFIC_RATIO = {"project": 1.000, "update": 0.992, "orth": 0.996}
-NCU_TRAFFIC_SOURCE = "profiles/r01b_ncu_full_summary.txt, profiles/r02_ncu_traffic_by_k.txt"
+# profiles/r02_ncu_traffic_by_k.txt — the fused orthogonalisation kernel at 30 / 70 / 110 columns (n = 16.7 M):
+# 8.98 / 8.99, 19.93 / 19.73, 30.67 / 30.47 GB = 0.999, 1.010, 1.007; the same ratio at the per-GPU shape of an 8-GPU
+# run (n = 2.1 M per GPU) is in profiles/r02_ncu_traffic_8gpu_shape.txt.  Separate kernels (LLZ_FUSED_ORTH=0):
+# profiles/r01b_ncu_full_summary.txt.
+NCU_TRAFFIC_RATIO = {"project": 1.000, "update": 0.992, "orth": 1.005}
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_traffic_by_k.txt, profiles/r02_ncu_traffic_8gpu_shape.txt, profiles/r01b_ncu_full_summary.txt"
 
 METRIC = "lanczos_iterations_per_second"
 UNIT = "iterations/s"
