@@ -57,7 +57,12 @@ typedef enum {
   LLZ_ORTH_RECURRENCE = 0, /* three-term recurrence only          (exponentiator.hpp:112-118, full_orthogonalize=false) */
   LLZ_ORTH_FULL = 1,       /* recurrence + one classical Gram-Schmidt pass against [locked, basis]
                               (replaces the MGS sweeps of lambda_lanczos.hpp:259-260, exponentiator.hpp:120-122) */
-  LLZ_ORTH_FULL_TWICE = 2  /* as FULL, followed by a second projection pass (CGS2) */
+  LLZ_ORTH_FULL_TWICE = 2, /* as FULL, followed by a second projection pass (CGS2) */
+  LLZ_ORTH_RECURRENCE_LAZY = 3 /* RECURRENCE without the normalisation pass (2 n s bytes per iteration less): column k >= 1
+                              is stored as beta_{k-1} u_k, the recurrence of the next iterations absorbs the factors
+                              (w = A(beta u)/beta ...), alpha / beta are reported as usual; the caller divides the
+                              coefficient of column k by beta_{k-1} in llz_krylov_combine.  Single rank only; every
+                              iteration of a run must use it (what Exponentiator<T>::run does, exponentiator.hpp:106-160) */
 } llz_orth_t;
 
 int llz_version(void);

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "libllz.so")
 F32, F64, C64, C128 = 0, 1, 2, 3
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64, np.dtype(np.complex128): C128}
 _NP = {F32: np.float32, F64: np.float64, C64: np.complex64, C128: np.complex128}
-ORTH_RECURRENCE, ORTH_FULL, ORTH_FULL_TWICE = 0, 1, 2
+ORTH_RECURRENCE, ORTH_FULL, ORTH_FULL_TWICE, ORTH_RECURRENCE_LAZY = 0, 1, 2, 3
 
 i64 = C.c_int64
 vp = C.c_void_p

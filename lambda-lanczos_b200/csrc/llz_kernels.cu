@@ -596,6 +596,13 @@ struct RecurrenceArgs {
   PeerMsg alpha_msg;
   PeerMsg norm_msg;
   GatherPush push;
+  // lazy normalisation (LLZ_ORTH_RECURRENCE_LAZY): u1 / u2 are stored scaled by *scale1 / *scale2 (null: 1), w = A u1
+  // carries scale1 too; the output stays un-normalised and the LAST CTA finishes ||out|| and publishes per `sink`
+  int lazy;
+  const double* scale1;
+  const double* scale2;
+  ScalarSink sink;
+  unsigned int* ticket;
 };
 
 template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(RecurrenceArgs a) {
@@ -612,9 +619,78 @@ template <class T> __global__ void __launch_bounds__(kThreads, 4) k_recurrence(R
     } else {
       al = block_sum_partials(a.pa, a.npa, scratch);
     }
+    R cw = (R)1;  // factor of w (lazy mode)
+    double alpha_true = al;
+    if (a.lazy) {
+      // stored: x~ = s1 u1, u2~ = s2 u2, w~ = A x~.  With beta_prev = s1:
+      //   r = w~/s1 - (alpha~/s1^3) x~ - (s1/s2) u2~,   alpha = alpha~/s1^2
+      const double s1 = a.scale1 ? *a.scale1 : 1.0, s2 = a.scale2 ? *a.scale2 : 1.0;
+      alpha_true = al / (s1 * s1);
+      cw = (R)(1.0 / s1);
+      al = alpha_true / s1;
+      if (a.fold >= 2) beta = (R)(s1 / s2);
+    } else if (a.fold >= 2) {
+      beta = (R)(*a.beta_prev);
+    }
     alpha = (R)al;
-    if (blockIdx.x == 0 && tid == 0 && a.alpha_out) *a.alpha_out = al;
-    if (a.fold >= 2) beta = (R)(*a.beta_prev);
+    if (blockIdx.x == 0 && tid == 0 && a.alpha_out) *a.alpha_out = alpha_true;
+    if (a.lazy) {
+      const T* w = reinterpret_cast<const T*>(a.w);
+      const T* u1 = reinterpret_cast<const T*>(a.u1);
+      const T* u2 = reinterpret_cast<const T*>(a.u2);
+      T* out = reinterpret_cast<T*>(a.out);
+      const int64_t npacks = (a.n + VEC - 1) / VEC;
+      double nrm = 0.0;
+      for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < npacks; p += (int64_t)gridDim.x * kThreads) {
+        const int64_t idx = p * VEC;
+        const bool full = idx + VEC <= a.n;
+        Pack<T> acc = full ? ld_plain(w + idx) : ld_guard(w, idx, a.n);
+        Pack<T> v = full ? ld_stream(u1 + idx) : ld_guard(u1, idx, a.n);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          acc.e[e] = scale_real(acc.e[e], cw);
+          fnma_real(acc.e[e], alpha, v.e[e]);
+        }
+        if (a.fold >= 2) {
+          Pack<T> v2 = full ? ld_stream(u2 + idx) : ld_guard(u2, idx, a.n);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) fnma_real(acc.e[e], beta, v2.e[e]);
+        }
+        if (full)
+          st_pack(out + idx, acc);
+        else
+          st_guard(out, idx, a.n, acc);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) nrm += abs2(acc.e[e]);
+      }
+      // per-CTA partial; the last CTA to arrive sums them in index order (every run: the same bits) and publishes
+      const double t = block_sum(nrm, scratch);
+      __shared__ int last_cta;
+      if (tid == 0) {
+        a.pb[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int tk = atomicAdd(a.ticket, 1u);
+        last_cta = (tk == gridDim.x - 1);
+        if (last_cta) *a.ticket = 0;
+      }
+      __syncthreads();
+      if (!last_cta) return;
+      __threadfence();
+      double v = 0.0;
+      for (int i = tid; i < (int)gridDim.x; i += kThreads) v += __ldcg(a.pb + i);
+      const double beta_new = sqrt(block_sum(v, scratch));
+      if (tid == 0) {
+        if (a.sink.beta_out) *a.sink.beta_out = beta_new;
+        if (a.sink.h_beta) *a.sink.h_beta = beta_new;
+        if (a.sink.h_alpha) *a.sink.h_alpha = alpha_true;
+        if (a.sink.h_wnorm) *a.sink.h_wnorm = beta_new;
+        if (a.sink.h_flag) {
+          __threadfence_system();
+          *reinterpret_cast<volatile long long*>(a.sink.h_flag) = a.sink.flag_value;
+        }
+      }
+      return;
+    }
   }
   const T* w = reinterpret_cast<const T*>(a.w);
   const T* u1 = reinterpret_cast<const T*>(a.u1);
@@ -1157,8 +1233,13 @@ int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const dou
 }
 
 int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, const void* u2, void* out, int64_t n,
-                      const Fold& fold, double* norm_partials, int* grid_out) {
+                      const Fold& fold, double* norm_partials, int* grid_out, const LazyRecurrence* lazy) {
   RecurrenceArgs a;
+  a.lazy = lazy ? 1 : 0;
+  a.scale1 = lazy ? lazy->scale1 : nullptr;
+  a.scale2 = lazy ? lazy->scale2 : nullptr;
+  if (lazy) a.sink = lazy->sink;
+  a.ticket = lazy ? lazy->ticket : nullptr;
   a.w = w;
   a.u1 = u1;
   a.u2 = u2;

@@ -82,6 +82,7 @@ struct llz_krylov_s {
   void* d_ycoef = nullptr;  // combine coefficients (device, T)
   size_t ycoef_cap = 0;
   double* d_misc = nullptr;
+  unsigned int* d_ticket = nullptr;  // last-CTA detection of the lazy recurrence kernel
   double* h_alpha = nullptr;  // pinned + mapped
   double* h_beta = nullptr;
   double* h_misc = nullptr;
@@ -326,6 +327,8 @@ static int krylov_init(llz_krylov_t kry, int dtype, int64_t n, int64_t max_cols)
   LLZ_CUDA(cudaMalloc(&kry->d_pa, kMaxGrid * sizeof(double)));
   LLZ_CUDA(cudaMalloc(&kry->d_pb, (size_t)kMaxGrid * 5 * sizeof(double)));
   LLZ_CUDA(cudaMalloc(&kry->d_misc, 8 * sizeof(double)));
+  LLZ_CUDA(cudaMalloc(&kry->d_ticket, sizeof(unsigned int)));
+  LLZ_CUDA(cudaMemsetAsync(kry->d_ticket, 0, sizeof(unsigned int), ctx->stream));
   kry->coef_cap = (sc + 64) * 2;
   LLZ_CUDA(cudaMalloc(&kry->d_coef, kry->coef_cap * sizeof(double)));
   LLZ_CUDA(cudaHostAlloc(&kry->h_alpha, sc * sizeof(double), cudaHostAllocMapped));
@@ -373,6 +376,7 @@ void llz::krylov_destroy_now(llz_krylov_t kry) {
   cudaFree(kry->d_pa);
   cudaFree(kry->d_pb);
   cudaFree(kry->d_misc);
+  if (kry->d_ticket) cudaFree(kry->d_ticket);
   cudaFree(kry->d_coef);
   if (kry->d_ph) cudaFree(kry->d_ph);
   if (kry->d_ycoef) cudaFree(kry->d_ycoef);
@@ -515,6 +519,24 @@ int llz_krylov_step(llz_krylov_t kry, llz_op_t op, double sigma, int orth) {
     kry->pushed_col = k;
     kry->pushed_op = op->impl;
     kry->pushed = fold.push;
+  }
+  if (orth == LLZ_ORTH_RECURRENCE_LAZY) {
+    if (ctx->nranks > 1) return fail(LLZ_ERR_UNSUPPORTED, "krylov_step: LLZ_ORTH_RECURRENCE_LAZY is for a single rank");
+    LazyRecurrence lazy;
+    lazy.scale1 = (k >= 2) ? kry->d_beta + (k - 2) : nullptr;  // column j >= 1 is stored as beta_{j-1} u_j, column 0 is normalised
+    lazy.scale2 = (k >= 3) ? kry->d_beta + (k - 3) : nullptr;
+    lazy.ticket = kry->d_ticket;
+    lazy.sink.beta_out = kry->d_beta + (k - 1);
+    lazy.sink.h_alpha = kry->h_alpha + (k - 1);
+    lazy.sink.h_beta = kry->h_beta + (k - 1);
+    lazy.sink.h_wnorm = kry->h_wnorm + (k - 1);
+    lazy.sink.h_flag = kry->h_flag;
+    lazy.sink.flag_value = k;
+    ProfScope ps(ctx, "recurrence", (double)kry->n * (double)dtype_size(kry->dtype) * (2 + fold.mode));
+    LLZ_TRY(launch_recurrence(ctx, kry->dtype, y, kry->col(k - 1), k >= 2 ? kry->col(k - 2) : nullptr, y, kry->n, fold, kry->d_pb, &grid,
+                              &lazy));
+    kry->k = k;
+    return LLZ_OK;
   }
   if (orth == LLZ_ORTH_RECURRENCE) {
     fold.norm_msg = sink.beta_msg;

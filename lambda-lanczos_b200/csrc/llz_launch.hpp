@@ -95,8 +95,17 @@ int launch_orth(llz_ctx_t ctx, int dtype, const ColumnSet& cs, void* w, int64_t 
 int launch_scale_by_norm(llz_ctx_t ctx, int dtype, void* x, int64_t n, const double* norm_partials, int n_partials,
                          const ScalarSink& sink);
 // out = w - alpha u1 - beta u2 (no reorthogonalisation; exponentiator.hpp:112-118) + norm partials
+// `lazy` (LLZ_ORTH_RECURRENCE_LAZY, single rank): u1 / u2 / w are stored scaled by *scale1 / *scale2 / *scale1 (null: 1),
+// `out` stays un-normalised, and the kernel's last CTA finishes ||out|| and publishes the iteration's scalars per `sink`
+// — no normalisation pass follows.
+struct LazyRecurrence {
+  const double* scale1 = nullptr;
+  const double* scale2 = nullptr;
+  ScalarSink sink;
+  unsigned int* ticket = nullptr;
+};
 int launch_recurrence(llz_ctx_t ctx, int dtype, const void* w, const void* u1, const void* u2, void* out, int64_t n,
-                      const Fold& fold, double* norm_partials, int* grid_out);
+                      const Fold& fold, double* norm_partials, int* grid_out, const LazyRecurrence* lazy = nullptr);
 // out_r (+)= sum_j coef[r*ldc + j] col_j for r < nvec (<= 5); coef is a DEVICE array of T; norm partials per vector
 // at norm_partials[r*kMaxGrid + cta] when non-null.
 int launch_combine(llz_ctx_t ctx, int dtype, const void* V, int64_t ld, int col0, int ncols, const void* coef,

@@ -59,7 +59,11 @@ class Exponentiator {
 
     std::vector<double> alpha, beta;
     std::vector<T> coeff_prev;
-    const int orth = full_orthogonalize ? LLZ_ORTH_FULL : LLZ_ORTH_RECURRENCE;
+    // Without reorthogonalisation nothing but the next two iterations reads a Lanczos vector before the final sum, so on
+    // one GPU the vectors stay un-normalised (column l >= 1 holds beta_{l-1} u_l: no normalisation pass, 2 n s bytes per
+    // iteration less) and the sum below divides its coefficients by those factors.
+    const bool lazy = !full_orthogonalize && ctx.nranks() == 1;
+    const int orth = full_orthogonalize ? LLZ_ORTH_FULL : (lazy ? LLZ_ORTH_RECURRENCE_LAZY : LLZ_ORTH_RECURRENCE);
     const double beta_threshold = (double)std::numeric_limits<R>::epsilon();  // :154
     size_t itern = max_iteration;
     size_t enqueued = 0;
@@ -108,7 +112,10 @@ class Exponentiator {
 
     // :163-170 — output = ||input|| * sum_l coeff_prev[l] u_l
     std::vector<T> scaled(coeff_prev.size());
-    for (size_t l = 0; l < coeff_prev.size(); ++l) scaled[l] = T((R)input_norm) * coeff_prev[l];
+    for (size_t l = 0; l < coeff_prev.size(); ++l) {
+      scaled[l] = T((R)input_norm) * coeff_prev[l];
+      if (lazy && l >= 1) scaled[l] /= T((R)beta[l - 1]);
+    }
     llz_vec_t out = output.get();
     check(llz_krylov_combine(kry, (int64_t)scaled.size(), 1, scaled.data(), 0, &out), "llz_krylov_combine");
     last_iterations_ = itern;

@@ -309,6 +309,35 @@ def test_lanczos_vectors_match_oracle_iteration_by_iteration(pkg, ctx, wl, oracl
             assert abs(abs(np.vdot(ref.basis[j], V[j])) - 1.0) < 1e-9, j
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_lazy_recurrence_is_the_recurrence_without_the_normalisation_pass(pkg, ctx, wl, dtype):
+    """LLZ_ORTH_RECURRENCE_LAZY (what the Exponentiator runs on one GPU): same alpha_k, beta_k to rounding, column k
+    stored as beta_{k-1} u_k."""
+    csr = wl.peierls_csr(30, 27) if np.dtype(dtype).kind == "c" else wl.random_symmetric_csr(6007, 7, dtype=dtype)
+    csr = (csr[0], csr[1], csr[2].astype(dtype))
+    n = csr[0].size - 1
+    op = pkg.Operator.csr(ctx, *csr)
+    start = wl.start_vector(n, dtype)
+    steps = 12
+    out = {}
+    for mode in (pkg.ORTH_RECURRENCE, pkg.ORTH_RECURRENCE_LAZY):
+        kry = pkg.Krylov(ctx, dtype, n, steps + 2)
+        kry.begin(start)
+        ab = []
+        for k in range(1, steps + 1):
+            kry.step(op, 0.25, mode)
+            ab.append(kry.fetch(k))
+        out[mode] = (np.array(ab), [kry.column(j) for j in range(steps + 1)])
+        kry.close()
+    tol = 2e-5 if np.dtype(dtype) == np.float32 else 1e-12
+    ab0, cols0 = out[pkg.ORTH_RECURRENCE]
+    ab1, cols1 = out[pkg.ORTH_RECURRENCE_LAZY]
+    assert np.allclose(ab0, ab1, rtol=tol, atol=tol)
+    for j in range(steps + 1):
+        scale = 1.0 if j == 0 else ab1[j - 1, 1]
+        assert np.allclose(cols1[j] / scale, cols0[j], rtol=0, atol=50 * tol), j
+
+
 # ---- LambdaLanczos::run against the checker --------------------------------------------------------------------
 def run_both(pkg, ctx, checker, csr, dtype, start, **kw):
     n = csr[0].size - 1
