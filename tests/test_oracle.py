@@ -201,7 +201,7 @@ def _need_ref(oracle_mod):
     return oracle_mod.Reference()
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
 def test_restatement_matches_reference_units(oracle_mod, port, dtype):
     ref = _need_ref(oracle_mod)
     rs = np.random.RandomState(3)
@@ -231,7 +231,7 @@ def test_restatement_matches_reference_tridiagonal(oracle_mod, port):
         assert np.array_equal(e1, e2) and np.array_equal(q1, q2)
 
 
-@pytest.mark.parametrize("case", ["random_sym", "laplacian", "peierls", "xxz", "random_sym_f32"])
+@pytest.mark.parametrize("case", ["random_sym", "laplacian", "peierls", "xxz", "random_sym_f32", "peierls_c64"])
 def test_restatement_matches_reference_runs(oracle_mod, port, wl, case):
     ref = _need_ref(oracle_mod)
     if case == "random_sym":
@@ -242,6 +242,9 @@ def test_restatement_matches_reference_runs(oracle_mod, port, wl, case):
         csr, kw, dt = wl.laplacian2d_csr(20), dict(find_max=False, num_eigs=4), np.float64
     elif case == "peierls":
         csr, kw, dt = wl.peierls_csr(16, 16), dict(find_max=False, num_eigs=2), np.complex128
+    elif case == "peierls_c64":  # std::complex<float>: lambda_lanczos.hpp:109, util/common.hpp:80-102
+        full = wl.peierls_csr(14, 12, flux=0.05, trap=0.3)
+        csr, kw, dt = (full[0], full[1], full[2].astype(np.complex64)), dict(find_max=False, num_eigs=2), np.complex64
     else:
         csr, kw, dt = wl.xxz_csr(12), dict(find_max=False, num_eigs=1), np.float64
     n = csr[0].size - 1
@@ -255,12 +258,37 @@ def test_restatement_matches_reference_runs(oracle_mod, port, wl, case):
 
 def test_restatement_matches_reference_expm(oracle_mod, port, wl):
     ref = _need_ref(oracle_mod)
-    csr = wl.xxz_csr(10, dtype=np.complex128)
-    x = wl.neel_state(10)
-    for kw in (dict(), dict(full_orth=True), dict(taylor=True)):
-        i1, o1 = port.expm(*csr, -0.1j, x, **kw)
-        i2, o2 = ref.expm(*csr, -0.1j, x, **kw)
-        assert i1 == i2 and np.array_equal(o1, o2)
+    for dt in (np.complex128, np.complex64):
+        csr = wl.xxz_csr(10, dtype=dt)
+        x = wl.neel_state(10).astype(dt)
+        for kw in (dict(), dict(full_orth=True), dict(taylor=True)):
+            i1, o1 = port.expm(*csr, -0.1j, x, **kw)
+            i2, o2 = ref.expm(*csr, -0.1j, x, **kw)
+            assert i1 == i2 and np.array_equal(o1, o2), (dt, kw)
+
+
+def test_run_iteration_spy_agrees_with_the_run_it_spies_on(oracle_mod, wl):
+    """The shim's run_iteration spy (what bench.py's in-line parity block and the full-size GPU tests compare with): its
+    alpha_k, beta_k and Ritz values are those of the reference's own run on the same input, and the captured Lanczos
+    vectors are orthonormal and satisfy the three-term recurrence A u_k = beta_{k-1} u_{k-1} + alpha_k u_k + beta_k u_{k+1}."""
+    ref = _need_ref(oracle_mod)
+    csr = wl.laplacian2d_csr(24, 19)
+    n = csr[0].size - 1
+    start = wl.start_vector(n)
+    m = 14
+    r = ref.run_iteration(*csr, find_max=False, max_iter=m, init=start, capture=m)
+    full = ref.lanczos(*csr, find_max=False, num_eigs=1, max_iter=m, init=start)
+    assert full.iter_counts == [m] and r["iterations"] == m
+    assert abs(r["eigenvalues"][0] - full.eigenvalues[0]) <= 1e-14 * abs(full.eigenvalues[0])
+    V = np.array(r["basis"][:m])
+    assert np.abs(V @ V.T - np.eye(m)).max() < 1e-13
+    alpha, beta = r["alpha"][:m], r["beta"][:m - 1]
+    for k in range(1, m - 1):
+        lhs = wl.csr_matvec(*csr, V[k])
+        rhs = beta[k - 1] * V[k - 1] + alpha[k] * V[k] + beta[k] * V[k + 1]
+        assert np.linalg.norm(lhs - rhs) < 1e-12, k
+    T = np.diag(alpha) + np.diag(beta, 1) + np.diag(beta, -1)
+    assert abs(np.linalg.eigvalsh(T)[0] - r["eigenvalues"][0]) < 1e-13
 
 
 # ---- restatement vs committed fixtures generated from the compiled reference -------------------------------------
