@@ -250,6 +250,40 @@ void LAZY_EXPONENTIATOR_MATCHES_THE_EXACT_EXPONENTIAL() {
   CHECK(std::sqrt(diff / nrm) < 1e-13);
 }
 
+// Exponentiator with full reorthogonalisation: same iteration count and output for every depth (the speculative
+// iterations past the stopping test are never read)
+void EXPONENTIATOR_DEPTH_DOES_NOT_CHANGE_RESULTS() {
+  const size_t n = 64;
+  const auto a = random_symmetric(n, 5);
+  auto mv = [&](const vector<double>& in, vector<double>& out) {
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < n; ++j) out[i] += 0.1 * a[i][j] * in[j];
+  };
+  vector<double> input(n);
+  seeded(input);
+  vector<double> first;
+  size_t it_first = 0;
+  for (int full = 0; full < 2; ++full)
+    for (int depth : {0, 1, 3, -1}) {
+      Exponentiator<double> ex(mv, n);
+      ex.full_orthogonalize = full != 0;
+      ex.pipeline_depth = depth;
+      vector<double> output;
+      const size_t it = ex.run(-0.7, input, output);
+      if (first.empty()) {
+        first = output;
+        it_first = it;
+      }
+      double diff = 0, nrm = 0;
+      for (size_t i = 0; i < n; ++i) {
+        diff += (output[i] - first[i]) * (output[i] - first[i]);
+        nrm += first[i] * first[i];
+      }
+      CHECK(std::sqrt(diff / nrm) < (full ? 1e-10 : 1e-13));  // (with / without reorthogonalisation: rounding apart)
+      CHECK(it == it_first || full);
+    }
+}
+
 void AUTO_DEPTH() {
   CHECK(ll::auto_pipeline_depth(800000, true) == 4);                    // config 1: 100 k doubles
   CHECK(ll::auto_pipeline_depth((size_t)16 << 20, true) == 2);          // config 2 on 8 GPUs
@@ -272,6 +306,7 @@ int main() {
     RUN(A_FULL_BASIS_IS_AN_ERROR_NOT_A_HANG);
     RUN(A_THROWING_OPERATOR_SURFACES_AS_AN_ERROR);
     RUN(LAZY_EXPONENTIATOR_MATCHES_THE_EXACT_EXPONENTIAL);
+    RUN(EXPONENTIATOR_DEPTH_DOES_NOT_CHANGE_RESULTS);
     RUN(AUTO_DEPTH);
   } catch (const std::exception& e) {
     std::printf("EXCEPTION: %s\n", e.what());
