@@ -284,6 +284,38 @@ void EXPONENTIATOR_DEPTH_DOES_NOT_CHANGE_RESULTS() {
     }
 }
 
+// The reference's own Exponentiator cases (test/exponentiator_test.cpp:106-222, periodic hopping chain n = 100, a = 3i):
+// the iteration counts are decided by host logic alone — 19 Krylov iterations, 37 Taylor terms, 2 / 1 for a = 0.
+void REFERENCE_EXPONENTIATOR_ITERATION_COUNTS() {
+  using cd = std::complex<double>;
+  const size_t n = 100;
+  const double t = -1.0;
+  auto mv = [&](const vector<cd>& in, vector<cd>& out) {
+    for (size_t i = 0; i < n; ++i) out[i] += t * (in[(i + 1) % n] + in[(i + n - 1) % n]);
+  };
+  vector<cd> input(n);
+  input[0] = cd(1, 2);
+  input[n - 1] = cd(1, 2);
+  input[n / 2] = cd(8, 2);
+  double nrm = 0;
+  for (auto& x : input) nrm += std::norm(x);
+  for (auto& x : input) x /= std::sqrt(nrm);
+  Exponentiator<cd> ex(mv, n);
+  vector<cd> krylov, taylor;
+  CHECK(ex.run(cd(0.0, 3.0), input, krylov) == 19);
+  CHECK(ex.taylor_run(cd(0.0, 3.0), input, taylor) == 37);
+  double diff = 0;
+  for (size_t i = 0; i < n; ++i) diff += std::norm(krylov[i] - taylor[i]);
+  CHECK(std::sqrt(diff) < 1e-7);
+  ex.full_orthogonalize = true;
+  vector<cd> same;
+  CHECK(ex.run(cd(0, 0), input, same) == 2);
+  diff = 0;
+  for (size_t i = 0; i < n; ++i) diff += std::norm(same[i] - input[i]);
+  CHECK(std::sqrt(diff) < 1e-14);
+  CHECK(ex.taylor_run(cd(0, 0), input, same) == 1);
+}
+
 void AUTO_DEPTH() {
   CHECK(ll::auto_pipeline_depth(800000, true) == 4);                    // config 1: 100 k doubles
   CHECK(ll::auto_pipeline_depth((size_t)16 << 20, true) == 2);          // config 2 on 8 GPUs
@@ -307,6 +339,7 @@ int main() {
     RUN(A_THROWING_OPERATOR_SURFACES_AS_AN_ERROR);
     RUN(LAZY_EXPONENTIATOR_MATCHES_THE_EXACT_EXPONENTIAL);
     RUN(EXPONENTIATOR_DEPTH_DOES_NOT_CHANGE_RESULTS);
+    RUN(REFERENCE_EXPONENTIATOR_ITERATION_COUNTS);
     RUN(AUTO_DEPTH);
   } catch (const std::exception& e) {
     std::printf("EXCEPTION: %s\n", e.what());
